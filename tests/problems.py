@@ -1,0 +1,229 @@
+"""Problem definitions shared by the oracle tests and the GPU parity tests.
+
+Each factory takes `ns`, a namespace providing SVector / SMatrix / abs2 (either oracle/ggp_oracle.py
+or the product's host module), and returns a dict with the arguments of
+`GrossPitaevskiiProblem(u0, lengths; ...)` and of `solve(prob, StrangSplitting(), tspan; dt, nsaves)`.
+The closures are the reference's own test / example closures (file:line cited per factory).
+"""
+from types import SimpleNamespace
+
+import numpy as np
+
+
+def _sumsq(ks):
+    s = 0
+    for k in ks:
+        s = s + k * k
+    return s
+
+
+def quick_start(ns, kerr=True, N=128, dtype=np.complex128):
+    """examples/quick_start.jl:16-17,35,48,63-70,90-101 (BASELINE config C1)."""
+    L = 8
+    dL = L / N
+    rs = np.arange(N) * dL
+    X, Y = np.meshgrid(rs, rs, indexing="xy")   # numpy (y, x): x fastest == Julia first index
+    u0 = np.exp(-(X - L / 2) ** 2 - (Y - L / 2) ** 2).astype(dtype)
+
+    def dispersion(ks, param):
+        return _sumsq(ks) / 2
+
+    def nonlinearity(u, param):
+        return param.g * ns.abs2(u[0])
+
+    kw = dict(dispersion=dispersion)
+    tspan = (0, 1)
+    if kerr:
+        kw.update(nonlinearity=nonlinearity, param=SimpleNamespace(g=-6))
+        tspan = (0, 0.4)
+    return dict(u0=(u0,), lengths=(L, L), kwargs=kw, tspan=tspan, dt=0.01, nsaves=64)
+
+
+def bistability(ns, wrap=(0, 0, 0), n=256, nsaves=512, tspan=(0, 3300), dt=0.05):
+    """test/bistability_cycle.jl:1-55; wrap selects scalar / SVector{1} / SMatrix{1,1} wrappers
+    for (dispersion, nonlinearity, pump) as in :28-35,67-71."""
+    w0, g, delta, kz, gamma = 1483, 0.01, 0.3, 27, 0.1
+    wp = w0 + delta
+    L = 256
+    Imax, width = 0.6, 50
+    tmax = tspan[-1]
+    param = SimpleNamespace(tmax=tmax, Imax=Imax, width=width, wp=wp, w0=w0, kz=kz, gamma=gamma, g=g, L=L)
+
+    def dispersion(ks, p):
+        return -1j * p.gamma / 2 + p.w0 * (1 + _sumsq(ks) / (2 * p.kz ** 2)) - p.wp
+
+    def nonlinearity(psi, p):
+        return p.g * ns.abs2(psi)
+
+    def I(t, tmax, Imax):
+        val = -Imax * t * (t - tmax) * 4 / tmax ** 2
+        return 0.0 if val < 0 else val
+
+    def pump(x, p, t):
+        s = 0
+        for xi in x:
+            s = s + (xi - p.L / 2) ** 2
+        return np.exp(-s / p.width ** 2) * np.sqrt(I(t, p.tmax, p.Imax))
+
+    def wrapv(f):
+        return lambda *a: ns.SVector(_first(f(*a)))
+
+    def wrapm(f):
+        return lambda *a: ns.SMatrix([[_first(f(*a))]])
+
+    def _first(v):
+        return v[0] if isinstance(v, ns.SVector) else v
+
+    fs = []
+    for f, w in zip((dispersion, nonlinearity, pump), wrap):
+        fs.append(f if w == 0 else (wrapv(f) if w == 1 else wrapm(f)))
+    u0 = (np.zeros(n, dtype=np.complex128),)
+    return dict(u0=u0, lengths=(L,), kwargs=dict(dispersion=fs[0], nonlinearity=fs[1], pump=fs[2], param=param),
+                tspan=tspan, dt=dt, nsaves=nsaves, I=I, delta=delta, g=g, gamma=gamma, Imax=Imax)
+
+
+def exciton_polariton(ns, N=128, nsaves=256, tspan=(0, 100), dt=1e-1, dtype=np.complex128, time_pump=False):
+    """test/exciton_polariton_test.jl:1-46."""
+    hbar = 0.654
+    Wr = 5.07 / (2 * hbar)
+    gx = 0.0015 / hbar
+    gc = 0.07 / 0.6571 / hbar
+    wx = 1484.44 / hbar
+    wc = 1482.76 / hbar
+    m = hbar ** 2 / (2 * 2e-1)
+    wp = wc
+    dx_ = wp - wx
+    dc_ = wp - wc
+    A, w, g = 2, 100, 1e-2 / hbar
+    L = 256
+    param = SimpleNamespace(hbar=hbar, m=m, wc=wc, dc=dc_, gc=gc, dx=dx_, gx=gx, Wr=Wr, A=A, w=w, g=g, L=L,
+                            tmax=tspan[-1])
+
+    def dispersion(k, p):
+        Dcc = p.hbar * _sumsq(k) / (2 * p.m) - p.dc - 1j * p.gc
+        Dxx = -p.dx - 1j * p.gx
+        Dxc = p.Wr
+        return ns.SMatrix([[Dcc, Dxc], [Dxc, Dxx]])
+
+    def nonlinearity(psi, p):
+        return ns.SVector(0, p.g * ns.abs2(psi[1]))
+
+    def pump(r, p, t):
+        s = 0
+        for ri in r:
+            s = s + (ri - p.L / 2) ** 2
+        amp = 1.0
+        if time_pump:  # examples/bistability.jl:71-74 envelope, used by BASELINE config C3
+            val = -t * (t - p.tmax) * 4 / p.tmax ** 2
+            amp = np.sqrt(val) if val > 0 else 0.0
+        return ns.SVector(p.A * np.exp(-s / p.w ** 2) * amp, 0)
+
+    u0 = (np.zeros((N, N), dtype=dtype), np.zeros((N, N), dtype=dtype))
+    return dict(u0=u0, lengths=(L, L), kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, pump=pump,
+                                                   param=param),
+                tspan=tspan, dt=dt, nsaves=nsaves, param=param)
+
+
+def windowed_ft(ns, ntraj=10 ** 4, N=64):
+    """test/windowed_ft.jl:23-29,62-90."""
+    L = 20
+    dL = L / N
+    hbar = 0.6582
+    gamma = 0.1 / hbar
+    m = hbar ** 2 / 2.5
+    d0 = 0.49 / hbar
+    dt = 4
+    param = SimpleNamespace(d0=d0, m=m, gamma=gamma, hbar=hbar, L=L, dL=dL, N=N, dt=dt)
+
+    def dispersion(ks, p):
+        return -1j * p.gamma / 2 + p.hbar * _sumsq(ks) / (2 * p.m) - p.d0
+
+    def position_noise_func(psi, r, p):
+        return np.sqrt(p.gamma / 2 / p.dL)
+
+    u0 = (np.zeros((ntraj, N), dtype=np.complex128),)
+    noise_prototype = tuple(np.empty_like(x) for x in u0)
+    return dict(u0=u0, lengths=(L,), kwargs=dict(dispersion=dispersion, param=param,
+                                                 position_noise_func=position_noise_func,
+                                                 noise_prototype=noise_prototype),
+                tspan=(0, 200), dt=dt, nsaves=1, save_start=False, L=L, N=N)
+
+
+def truncated_wigner(ns, ntraj=256, N=256, ndim=1, dtype=np.complex128, seed=1234, tspan=(0, 200), dt=0.05):
+    """examples/truncated_wigner.jl:33-50,93-99 (1-D as shipped; ndim=2 is BASELINE config C4)."""
+    hbar = 0.6582
+    gamma = 0.047 / hbar
+    m = 1 / 6
+    g = 3e-4 / hbar
+    delta = 0.49 / hbar
+    A = 10
+    L = 512
+    dx = L / N
+    vol = dx ** ndim
+    param = SimpleNamespace(hbar=hbar, m=m, delta=delta, gamma=gamma, g=g, A=A, L=L, dx=vol)
+
+    def dispersion(ks, p):
+        return p.hbar * _sumsq(ks) / (2 * p.m) - p.delta - 1j * p.gamma / 2
+
+    def pump(x, p, t):
+        return p.A
+
+    def nonlinearity(psi, p):
+        return p.g * (ns.abs2(psi[0]) - 1 / p.dx)
+
+    def position_noise_func(psi, xs, p):
+        return np.sqrt(p.gamma / (2 * p.dx))
+
+    rng = np.random.default_rng(seed)
+    shape = (ntraj,) + (N,) * ndim
+    z = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)
+    u0 = ((z / np.sqrt(2 * vol)).astype(dtype),)
+    noise_prototype = tuple(np.empty_like(x) for x in u0)
+    return dict(u0=u0, lengths=(L,) * ndim,
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, pump=pump, param=param,
+                            noise_prototype=noise_prototype, position_noise_func=position_noise_func),
+                tspan=tspan, dt=dt, nsaves=1, save_start=False, param=param)
+
+
+def kerr2d(ns, N=256, dtype=np.complex64, L=64.0, g=1.0, dt=1e-3, nsteps=100, seed=1234):
+    """BASELINE config C2 shape: 2-D scalar Kerr, D=|k|²/2, G=g|u|², Gaussian + 10 % noise."""
+    real = np.float32 if dtype == np.complex64 else np.float64
+    Lr = real(L)
+    rs = np.arange(N).astype(real) * (Lr / N)
+    X, Y = np.meshgrid(rs, rs, indexing="xy")
+    rng = np.random.default_rng(seed)
+    xi = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))) / np.sqrt(2)
+    u0 = (np.exp(-((X - Lr / 2) ** 2 + (Y - Lr / 2) ** 2) / 16) * (1 + 0.1 * xi)).astype(dtype)
+
+    def dispersion(ks, param):
+        return _sumsq(ks) / 2
+
+    def nonlinearity(u, param):
+        return param.g * ns.abs2(u[0])
+
+    dtr = real(dt)
+    return dict(u0=(u0,), lengths=(Lr, Lr),
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=SimpleNamespace(g=real(g))),
+                tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=1)
+
+
+def kerr3d(ns, N=32, dtype=np.complex64, L=32.0, g=1.0, dt=1e-3, nsteps=10, seed=1234):
+    """BASELINE config C5 shape: 3-D Kerr GPE."""
+    real = np.float32 if dtype == np.complex64 else np.float64
+    Lr = real(L)
+    rs = np.arange(N).astype(real) * (Lr / N)
+    Z, Y, X = np.meshgrid(rs, rs, rs, indexing="ij")
+    rng = np.random.default_rng(seed)
+    xi = (rng.standard_normal((N, N, N)) + 1j * rng.standard_normal((N, N, N))) / np.sqrt(2)
+    u0 = (np.exp(-((X - Lr / 2) ** 2 + (Y - Lr / 2) ** 2 + (Z - Lr / 2) ** 2) / 16) * (1 + 0.01 * xi)).astype(dtype)
+
+    def dispersion(ks, param):
+        return _sumsq(ks) / 2
+
+    def nonlinearity(u, param):
+        return param.g * ns.abs2(u[0])
+
+    dtr = real(dt)
+    return dict(u0=(u0,), lengths=(Lr, Lr, Lr),
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=SimpleNamespace(g=real(g))),
+                tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=1)
