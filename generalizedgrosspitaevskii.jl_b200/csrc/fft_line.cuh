@@ -1,0 +1,101 @@
+// One FFT line per group of TPL = N/E threads: every thread keeps E elements of the line in
+// registers (positions t + m*TPL, m = 0..E-1, coalesced across t), Stockham auto-sort passes of
+// radix E (last pass: the remainder radix), data exchanged between passes through a padded
+// shared-memory line.  First-pass inputs and last-pass outputs stay in registers, so
+//   * global loads/stores fuse into the first / last pass (no staging sweep),
+//   * a point-wise stage fuses between an inverse and a forward transform without touching smem.
+// Natural order in, natural order out -- tables and HBM layouts need no permutation.
+#pragma once
+#include "cplx.cuh"
+
+namespace ggp {
+
+__host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+
+// Elements per thread.  fp32: radix-16 passes (32 data registers); fp64: radix-8 (32 data
+// registers).  Long lines use a wider radix so that a line never needs more than 256 threads.
+template <typename T>
+__host__ __device__ constexpr int default_E(int N) {
+  int e = sizeof(T) == 4 ? 16 : 8;
+  while (N / e > 256) e *= 2;
+  return e < N ? e : N;
+}
+
+template <typename T, int N>
+struct LineCfg {
+  static constexpr int E = default_E<T>(N);
+  static constexpr int TPL = N / E;         // threads per line
+  static constexpr int LOGE = ilog2(E);
+  // padded length of one line in shared memory: one pad element per E elements keeps the
+  // scattered Stockham writes (stride R) and the strided reads conflict-free
+  static constexpr int PADN = N + N / E;
+  __host__ __device__ static constexpr int pad(int i) { return i + (i >> LOGE); }
+};
+
+struct SyncBlock {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct SyncWarp {
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+// Stockham pass PASS (NS = product of the radices of the earlier passes) and all later passes.
+// DIR = -1 forward (e^{-i k x}), +1 inverse (unnormalised).  tw[j] = exp(-2 pi i j / N).
+template <typename T, int N, int DIR, typename SYNC, int NS>
+struct Passes {
+  using Cfg = LineCfg<T, N>;
+  static constexpr int E = Cfg::E;
+  static constexpr int TPL = Cfg::TPL;
+  static constexpr int R = (N / NS >= E) ? E : N / NS;
+  static constexpr int NB = E / R;  // butterflies per thread in this pass
+  static constexpr bool LASTP = (NS * R == N);
+
+  static __device__ __forceinline__ void run(cpx<T> (&v)[E], const int t, cpx<T>* __restrict__ line,
+                                             const cpx<T>* __restrict__ tw) {
+    if constexpr (NS > 1) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = line[Cfg::pad(t + m * TPL)];
+      if constexpr (!LASTP) SYNC::sync();  // everybody has read before anybody overwrites
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      cpx<T> a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = v[q + r * NB];
+      const int b = t + q * TPL;
+      const int k = b & (NS - 1);
+      if constexpr (NS > 1) {
+        constexpr int TS = N / (NS * R);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          const cpx<T> w = tw[r * k * TS];
+          a[r] = DIR < 0 ? cmul(a[r], w) : cmulc(a[r], w);
+        }
+      }
+      Dft<T, R, DIR>::run(a);
+      if constexpr (LASTP) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[q + r * NB] = a[r];
+      } else {
+        const int base = (b - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) line[Cfg::pad(base + r * NS)] = a[r];
+      }
+    }
+    if constexpr (!LASTP) {
+      SYNC::sync();
+      Passes<T, N, DIR, SYNC, NS * R>::run(v, t, line, tw);
+    }
+  }
+};
+
+// Transform one line held in registers.  PRESYNC: the shared line may still be read by a previous
+// transform of the same thread group, so synchronise before the first scatter.
+template <typename T, int N, int DIR, typename SYNC, bool PRESYNC>
+__device__ __forceinline__ void fft_line(cpx<T> (&v)[LineCfg<T, N>::E], const int t, cpx<T>* __restrict__ line,
+                                         const cpx<T>* __restrict__ tw) {
+  if (PRESYNC && LineCfg<T, N>::E < N) SYNC::sync();
+  Passes<T, N, DIR, SYNC, 1>::run(v, t, line, tw);
+}
+
+}  // namespace ggp

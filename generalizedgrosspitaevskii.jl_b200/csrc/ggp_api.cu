@@ -1,0 +1,769 @@
+// C ABI of libggp.so (include/ggp.h): plan management, table upload, step scheduling.
+// Replaces init / step! / the inner loop of solve! of the reference (src/strang_splitting.jl:32-90,
+// src/fixed_time_stepping.jl:38-50).  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ggp.h"
+#include "kernels.cuh"
+#include "sizes_gen.h"
+
+#ifdef GGP_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace ggp {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define GGP_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(GGP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+  } while (0)
+
+#define GGP_LAUNCH(expr, what)                                                                  \
+  do {                                                                                          \
+    int e__ = (expr);                                                                           \
+    if (e__ != 0)                                                                               \
+      return fail(GGP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)e__)); \
+  } while (0)
+
+// ---- size dispatch ---------------------------------------------------------------------------
+template <typename T>
+static int dispatch_row(int N, int M, bool pre, bool post, const RowParams<T>& p, cudaStream_t st) {
+  switch (N) {
+#define X(n) \
+  case n:    \
+    return launch_row<T, n>(M, pre, post, p, st);
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+template <typename T>
+static int dispatch_str(int N, int M, int mode, const StrParams<T>& p, long long nfast, long long nother,
+                        cudaStream_t st) {
+  switch (N) {
+#define X(n) \
+  case n:    \
+    return launch_str<T, n>(M, mode, p, nfast, nother, st);
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+template <typename T>
+static int dispatch_oned(int N, int M, const OneDParams<T>& p, cudaStream_t st) {
+  switch (N) {
+#define X(n) \
+  case n:    \
+    return launch_oned<T, n>(M, p, st);
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+static bool size_supported(long long n) {
+  switch (n) {
+#define X(n_) \
+  case n_:    \
+    return true;
+    GGP_SIZES(X)
+#undef X
+  }
+  return false;
+}
+
+// ---- observables -------------------------------------------------------------------------------
+template <typename T>
+__global__ void density_kernel(const cpx<T>* __restrict__ u, double* __restrict__ out, long long nspatial,
+                               long long nbatch, double scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nspatial) return;
+  double acc = 0;
+  for (long long b = 0; b < nbatch; ++b) {
+    const cpx<T> z = u[b * nspatial + i];
+    acc += (double)z.x * (double)z.x + (double)z.y * (double)z.y;
+  }
+  out[i] = acc * scale;
+}
+
+__global__ void sum_kernel(const double* __restrict__ in, double* __restrict__ out, long long n) {
+  __shared__ double sh[256];
+  double acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += in[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, sh[0]);
+}
+
+// ---- plan ----------------------------------------------------------------------------------------
+enum { KC_ROW = 0, KC_STR_D = 1, KC_STR_FI = 2, KC_ONED = 3, KC_COUNT = 4 };
+
+struct PlanBase {
+  virtual ~PlanBase() {}
+  virtual int create(const ggp_desc& d) = 0;
+  virtual int set_state(const void* const* u) = 0;
+  virtual int get_state(void* const* u) = 0;
+  virtual int step(int64_t nsteps, const double* amp, const void* const* noise) = 0;
+  virtual int observe(int kind, double* out) = 0;
+  virtual void* state_ptr(int c) = 0;
+
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  int64_t dev_bytes = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> pev;      // pairs
+  std::vector<int> pev_class;
+  double prof_ms[KC_COUNT] = {0, 0, 0, 0};
+  int64_t prof_n[KC_COUNT] = {0, 0, 0, 0};
+#ifdef GGP_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  int nranks = 1;
+
+  int prof_begin(int cls) {
+    if (!profiling) return 0;
+    cudaEvent_t a, b;
+    GGP_CUDA(cudaEventCreate(&a));
+    GGP_CUDA(cudaEventCreate(&b));
+    pev.push_back(a);
+    pev.push_back(b);
+    pev_class.push_back(cls);
+    GGP_CUDA(cudaEventRecord(a, stream));
+    return 0;
+  }
+  int prof_end() {
+    if (!profiling) return 0;
+    GGP_CUDA(cudaEventRecord(pev.back(), stream));
+    return 0;
+  }
+  int prof_collect() {
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < pev_class.size(); ++i) {
+      float ms = 0;
+      GGP_CUDA(cudaEventElapsedTime(&ms, pev[2 * i], pev[2 * i + 1]));
+      prof_ms[pev_class[i]] += ms;
+      prof_n[pev_class[i]] += 1;
+      cudaEventDestroy(pev[2 * i]);
+      cudaEventDestroy(pev[2 * i + 1]);
+    }
+    pev.clear();
+    pev_class.clear();
+    return 0;
+  }
+};
+
+template <typename T>
+struct PlanT : PlanBase {
+  int ndim = 0, M = 0;
+  long long n[3] = {1, 1, 1};
+  long long nspatial = 0, nbatch = 0, batch_offset = 0;
+  double dt = 0;
+  cpx<T>* u[2] = {nullptr, nullptr};
+  cpx<T>* D[4] = {nullptr, nullptr, nullptr, nullptr};
+  cpx<T>* V[4] = {nullptr, nullptr, nullptr, nullptr};
+  cpx<T>* S[2] = {nullptr, nullptr};
+  cpx<T>* tw[3] = {nullptr, nullptr, nullptr};
+  int dkind = 0;
+  PointwiseParams<T> pw;
+  bool has_pointwise = false;
+  int pump_kind = 0, noise_kind = 0, noise_real = 0;
+  std::complex<double> amp_prev = 0;
+  uint64_t half_ctr = 0;
+  HalfStep<T>* hs_dev = nullptr;
+  size_t hs_cap = 0;
+  void* xi_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  double* obs_dev = nullptr;
+  cpx<T>* scratch[2] = {nullptr, nullptr};
+  std::vector<void*> allocs;
+
+  ~PlanT() override {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (void* p : allocs) cudaFree(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t e : pev) cudaEventDestroy(e);
+#ifdef GGP_WITH_NCCL
+    if (comm) ncclCommDestroy(comm);
+#endif
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  int dalloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+      return fail(GGP_ERR_ALLOC, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    allocs.push_back(*p);
+    dev_bytes += (int64_t)bytes;
+    return 0;
+  }
+
+  // host AoS table (npts x ncols, `prec`) -> device SoA planes of T, scaled
+  int upload_table(const void* host, int prec, int ncols, double scale, cpx<T>** planes) {
+    std::vector<cpx<T>> tmp((size_t)nspatial);
+    for (int c = 0; c < ncols; ++c) {
+      if (prec == GGP_C128) {
+        const std::complex<double>* h = (const std::complex<double>*)host;
+        for (long long i = 0; i < nspatial; ++i) {
+          const std::complex<double> z = h[i * ncols + c] * scale;
+          tmp[(size_t)i] = mk<T>((T)z.real(), (T)z.imag());
+        }
+      } else {
+        const std::complex<float>* h = (const std::complex<float>*)host;
+        for (long long i = 0; i < nspatial; ++i) {
+          const std::complex<float> z = h[i * ncols + c];
+          tmp[(size_t)i] = mk<T>((T)((double)z.real() * scale), (T)((double)z.imag() * scale));
+        }
+      }
+      int rc = dalloc((void**)&planes[c], sizeof(cpx<T>) * (size_t)nspatial);
+      if (rc) return rc;
+      GGP_CUDA(cudaMemcpy(planes[c], tmp.data(), sizeof(cpx<T>) * (size_t)nspatial, cudaMemcpyHostToDevice));
+    }
+    return 0;
+  }
+
+  static int ncols_of(int kind, int M) {
+    return kind == GGP_TABLE_SCALAR ? 1 : kind == GGP_TABLE_DIAG ? M : kind == GGP_TABLE_FULL ? M * M : 0;
+  }
+
+  int create(const ggp_desc& d) override {
+    ndim = d.ndim;
+    M = d.ncomp;
+    nspatial = 1;
+    for (int i = 0; i < 3; ++i) n[i] = 1;
+    for (int i = 0; i < ndim; ++i) {
+      n[i] = d.n[i];
+      nspatial *= n[i];
+    }
+    nbatch = d.nbatch;
+    batch_offset = d.batch_offset;
+    dt = d.dt;
+    dkind = d.disp_kind;
+    if (dkind != GGP_TABLE_NONE)
+      for (int i = 0; i < ndim; ++i)
+        if (!size_supported(n[i]))
+          return fail(GGP_ERR_UNSUPPORTED, "FFT axis length " + std::to_string(n[i]) +
+                                               " is not a supported power of two (SURVEY §8f N4)");
+    if (d.pot_kind == GGP_TABLE_FULL && d.nl_kind != GGP_NL_NONE && !d.nl_scalar && M > 1)
+      return fail(GGP_ERR_INVALID,
+                  "SVector nonlinearity with SMatrix potential is a DimensionMismatch in the reference (src/kernels.jl:9)");
+
+    if (d.stream) {
+      stream = (cudaStream_t)d.stream;
+    } else {
+      GGP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      own_stream = true;
+    }
+    GGP_CUDA(cudaEventCreate(&ev0));
+    GGP_CUDA(cudaEventCreate(&ev1));
+
+    const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+    for (int c = 0; c < M; ++c) {
+      int rc = dalloc((void**)&u[c], bytes);
+      if (rc) return rc;
+      GGP_CUDA(cudaMemsetAsync(u[c], 0, bytes, stream));
+    }
+    // tables.  The inverse transform is unnormalised on the device; the reference's 1/prod(n)
+    // (ScaledPlan, src/misc.jl:56) is folded into exp_D -- exact for power-of-two sizes.
+    int rc;
+    if (dkind != GGP_TABLE_NONE) {
+      if (!d.disp_table) return fail(GGP_ERR_INVALID, "disp_table is NULL");
+      if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / (double)nspatial, D))) return rc;
+    }
+    {
+      for (int a = 0; a < ndim; ++a) {
+        for (int b = 0; b < a; ++b)
+          if (n[b] == n[a]) tw[a] = tw[b];
+        if (tw[a]) continue;
+        std::vector<cpx<T>> h((size_t)n[a]);
+        for (long long j = 0; j < n[a]; ++j) {
+          const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n[a];
+          h[(size_t)j] = mk<T>((T)cosl(ang), (T)sinl(ang));
+        }
+        if ((rc = dalloc((void**)&tw[a], sizeof(cpx<T>) * (size_t)n[a]))) return rc;
+        GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(cpx<T>) * (size_t)n[a], cudaMemcpyHostToDevice));
+      }
+    }
+    memset(&pw, 0, sizeof(pw));
+    pw.dt = (T)(dt / 2);
+    pw.sqrt_dt = (T)std::sqrt(dt / 2);
+    pw.vkind = d.pot_kind;
+    if (d.pot_kind != GGP_TABLE_NONE) {
+      if (!d.pot_table) return fail(GGP_ERR_INVALID, "pot_table is NULL");
+      if ((rc = upload_table(d.pot_table, d.table_precision, ncols_of(d.pot_kind, M), 1.0, V))) return rc;
+      for (int i = 0; i < 4; ++i) pw.expV[i] = V[i];
+    }
+    pump_kind = d.pump_kind;
+    if (pump_kind != GGP_PUMP_NONE) {
+      if (!d.pump_table) return fail(GGP_ERR_INVALID, "pump_table is NULL");
+      if (d.pump_ncomp != 1 && d.pump_ncomp != M) return fail(GGP_ERR_INVALID, "pump_ncomp must be 1 or ncomp");
+      if ((rc = upload_table(d.pump_table, d.table_precision, d.pump_ncomp, 1.0, S))) return rc;
+      pw.pump = d.pump_ncomp == 1 ? 1 : 2;
+      pw.S[0] = S[0];
+      pw.S[1] = S[1];
+      amp_prev = std::complex<double>(d.pump_amp0[0], d.pump_amp0[1]);
+    }
+    if (d.nl_kind == GGP_NL_DIAG) {
+      bool cplx = false;
+      for (int i = 0; i < M; ++i) {
+        const int src = d.nl_scalar ? 0 : i;
+        pw.nl_c_re[i] = (T)d.nl_c[src][0];
+        pw.nl_c_im[i] = (T)d.nl_c[src][1];
+        if (d.nl_c[src][1] != 0) cplx = true;
+        for (int j = 0; j < M; ++j) {
+          pw.nl_g_re[i][j] = (T)d.nl_g[src][j][0];
+          pw.nl_g_im[i][j] = (T)d.nl_g[src][j][1];
+          if (d.nl_g[src][j][1] != 0) cplx = true;
+        }
+      }
+      pw.nl = cplx ? 2 : 1;
+    }
+    noise_kind = d.noise_kind;
+    noise_real = d.noise_real;
+    if (noise_kind != GGP_NOISE_NONE) {
+      pw.noise = NOISE_PHILOX;
+      pw.noise_real = d.noise_real;
+      for (int i = 0; i < M; ++i) pw.eta[i] = mk<T>((T)d.noise_eta[i][0], (T)d.noise_eta[i][1]);
+      pw.seed_lo = (uint32_t)d.seed;
+      pw.seed_hi = (uint32_t)(d.seed >> 32);
+      pw.elem_offset = batch_offset * nspatial;
+    }
+    has_pointwise = pw.vkind || pw.pump || pw.nl || pw.noise;
+    if ((rc = dalloc((void**)&obs_dev, sizeof(double) * (size_t)(nspatial * M + 8)))) return rc;
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  int set_state(const void* const* uh) override {
+    const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+    for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(u[c], uh[c], bytes, cudaMemcpyHostToDevice, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_state(void* const* uh) override {
+    const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+    for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(uh[c], u[c], bytes, cudaMemcpyDeviceToHost, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  void* state_ptr(int c) override { return (c >= 0 && c < M) ? (void*)u[c] : nullptr; }
+
+  // half-step `half` (0/1) of the step whose pump amplitudes are (a_now, a_next)
+  HalfStep<T> make_half(std::complex<double> a_now, std::complex<double> a_next, int slot) {
+    HalfStep<T> h;
+    memset(&h, 0, sizeof(h));
+    const double q = dt / 4;  // (dt/2)/2, src/kernels.jl:45-46 with δt = dt/2
+    h.fnow = mk<T>((T)(q * a_now.real()), (T)(q * a_now.imag()));
+    h.fnext = mk<T>((T)(q * a_next.real()), (T)(q * a_next.imag()));
+    h.ctr = (uint32_t)half_ctr;
+    h.apply = has_pointwise ? 1 : 0;
+    h.xi[0] = xi_dev[slot][0];
+    h.xi[1] = xi_dev[slot][1];
+    ++half_ctr;
+    return h;
+  }
+
+  int upload_noise(const void* const* noise, int64_t s, int half, int slot) {
+    const size_t esz = noise_real ? sizeof(T) : sizeof(cpx<T>);
+    const size_t bytes = esz * (size_t)nspatial * (size_t)nbatch;
+    for (int c = 0; c < M; ++c) {
+      if (!xi_dev[slot][c]) {
+        int rc = dalloc(&xi_dev[slot][c], bytes);
+        if (rc) return rc;
+      }
+      GGP_CUDA(cudaMemcpyAsync(xi_dev[slot][c], noise[(s * 2 + half) * M + c], bytes, cudaMemcpyHostToDevice, stream));
+    }
+    return 0;
+  }
+
+  int run_row(bool pre, bool post, const HalfStep<T>& hA, const HalfStep<T>& hB) {
+    RowParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.u[0] = u[0];
+    p.u[1] = u[1];
+    p.tw = tw[0];
+    p.nlines = (nspatial / n[0]) * nbatch;
+    p.lines_per_image = nspatial / n[0];
+    p.pw = pw;
+    p.hA = hA;
+    p.hB = hB;
+    int rc = prof_begin(KC_ROW);
+    if (rc) return rc;
+    GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pre, post, p, stream), "row_kernel");
+    ++launches;
+    return prof_end();
+  }
+
+  // strided pass along axis `ax` (1 or 2)
+  int run_str(int ax, int mode) {
+    StrParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.u[0] = u[0];
+    p.u[1] = u[1];
+    p.tw = tw[ax];
+    for (int i = 0; i < 4; ++i) p.D[i] = D[i];
+    p.dkind = dkind;
+    long long nother;
+    if (ax == 1) {
+      p.ls = n[0];
+      p.no1 = n[2];
+      p.s1 = n[0] * n[1];
+      p.s2 = nspatial;
+      p.ts1 = n[0] * n[1];
+      nother = n[2] * nbatch;
+    } else {
+      p.ls = n[0] * n[1];
+      p.no1 = n[1];
+      p.s1 = n[0];
+      p.s2 = nspatial;
+      p.ts1 = n[0];
+      nother = n[1] * nbatch;
+    }
+    int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
+    if (rc) return rc;
+    GGP_LAUNCH(dispatch_str<T>((int)n[ax], M, mode, p, n[0], nother, stream), "str_kernel");
+    ++launches;
+    return prof_end();
+  }
+
+  int ensure_hs(size_t count) {
+    if (count <= hs_cap) return 0;
+    int rc = dalloc((void**)&hs_dev, sizeof(HalfStep<T>) * count);
+    if (rc) return rc;
+    hs_cap = count;
+    return 0;
+  }
+
+  int step(int64_t nsteps, const double* amp, const void* const* noise) override {
+    if (nsteps <= 0) return 0;
+    if (noise && noise_kind == GGP_NOISE_NONE) return fail(GGP_ERR_INVALID, "noise_host given but the plan has no noise term");
+    pw.noise = noise_kind == GGP_NOISE_NONE ? NOISE_OFF : (noise ? NOISE_HOST : NOISE_PHILOX);
+    auto amps = [&](int64_t s, int half) -> std::complex<double> {
+      if (pump_kind == GGP_PUMP_NONE) return 0.0;
+      if (!amp) return amp_prev;  // static pump
+      return std::complex<double>(amp[2 * (2 * s + half)], amp[2 * (2 * s + half) + 1]);
+    };
+    int rc;
+    if (ndim == 1) {
+      const int64_t chunk_max = noise ? 1 : 4096;
+      std::vector<HalfStep<T>> hs;
+      for (int64_t s0 = 0; s0 < nsteps; s0 += chunk_max) {
+        const int64_t cn = std::min<int64_t>(chunk_max, nsteps - s0);
+        hs.resize((size_t)(2 * cn));
+        for (int64_t s = 0; s < cn; ++s) {
+          const std::complex<double> a1 = amps(s0 + s, 0), a2 = amps(s0 + s, 1);
+          if (noise) {
+            if ((rc = upload_noise(noise, s0 + s, 0, 0))) return rc;
+            if ((rc = upload_noise(noise, s0 + s, 1, 1))) return rc;
+          }
+          hs[(size_t)(2 * s)] = make_half(amp_prev, a1, 0);
+          hs[(size_t)(2 * s + 1)] = make_half(a1, a2, 1);
+          amp_prev = a2;
+        }
+        if ((rc = ensure_hs((size_t)(2 * chunk_max)))) return rc;
+        GGP_CUDA(cudaMemcpyAsync(hs_dev, hs.data(), sizeof(HalfStep<T>) * hs.size(), cudaMemcpyHostToDevice, stream));
+        OneDParams<T> p;
+        memset(&p, 0, sizeof(p));
+        p.u[0] = u[0];
+        p.u[1] = u[1];
+        p.tw = tw[0];
+        p.nlines = nbatch;
+        p.pw = pw;
+        p.hs = hs_dev;
+        p.nsteps = (int)cn;
+        for (int i = 0; i < 4; ++i) p.D[i] = D[i];
+        p.dkind = dkind;
+        if ((rc = prof_begin(KC_ONED))) return rc;
+        GGP_LAUNCH(dispatch_oned<T>((int)n[0], M, p, stream), "oned_kernel");
+        ++launches;
+        if ((rc = prof_end())) return rc;
+      }
+      return 0;
+    }
+    // 2-D / 3-D
+    HalfStep<T> none;
+    memset(&none, 0, sizeof(none));
+    HalfStep<T> prev2 = none;
+    for (int64_t s = 0; s < nsteps; ++s) {
+      const std::complex<double> a1 = amps(s, 0), a2 = amps(s, 1);
+      if (noise && (rc = upload_noise(noise, s, 0, 0))) return rc;
+      const HalfStep<T> h1 = make_half(amp_prev, a1, 0);
+      if (dkind == GGP_TABLE_NONE) {
+        if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
+        const HalfStep<T> h2 = make_half(a1, a2, 1);
+        amp_prev = a2;
+        if (has_pointwise && (rc = run_row(false, false, h1, h2))) return rc;
+        continue;
+      }
+      if ((rc = run_row(s > 0, true, prev2, h1))) return rc;
+      if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
+      prev2 = make_half(a1, a2, 1);
+      amp_prev = a2;
+      if (ndim == 2) {
+        if ((rc = run_str(1, 1))) return rc;
+      } else {
+        if ((rc = run_str(1, 0))) return rc;
+        if ((rc = run_str(2, 1))) return rc;
+        if ((rc = run_str(1, 2))) return rc;
+      }
+    }
+    if (dkind != GGP_TABLE_NONE && (rc = run_row(true, false, prev2, none))) return rc;
+    return 0;
+  }
+
+  int observe(int kind, double* out) override {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((nspatial + threads - 1) / threads);
+    size_t count = 0;
+    if (kind == GGP_OBS_DENSITY) {
+      for (int c = 0; c < M; ++c) {
+        density_kernel<T><<<blocks, threads, 0, stream>>>(u[c], obs_dev + c * nspatial, nspatial, nbatch, 1.0);
+        ++launches;
+      }
+      count = (size_t)(nspatial * M);
+    } else if (kind == GGP_OBS_NORM) {
+      GGP_CUDA(cudaMemsetAsync(obs_dev + nspatial * M, 0, sizeof(double) * 8, stream));
+      for (int c = 0; c < M; ++c) {
+        density_kernel<T><<<blocks, threads, 0, stream>>>(u[c], obs_dev, nspatial, nbatch, 1.0);
+        sum_kernel<<<148, 256, 0, stream>>>(obs_dev, obs_dev + nspatial * M + c, nspatial);
+        launches += 2;
+      }
+      GGP_CUDA(cudaMemcpyAsync(obs_dev, obs_dev + nspatial * M, sizeof(double) * M, cudaMemcpyDeviceToDevice, stream));
+      count = (size_t)M;
+    } else if (kind == GGP_OBS_MOMENTUM) {
+      // n(k) = sum_traj |fft(u)(k)|^2 / N^2 (examples/truncated_wigner.jl:110-113): transform the state in
+      // place with the step's own FFT kernels, accumulate, then restore the saved copy.
+      for (int i = 0; i < ndim; ++i)
+        if (!size_supported(n[i])) return fail(GGP_ERR_UNSUPPORTED, "momentum observable needs power-of-two axes");
+      const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+      int rc;
+      for (int c = 0; c < M; ++c) {
+        if (!scratch[c] && (rc = dalloc((void**)&scratch[c], bytes))) return rc;
+        GGP_CUDA(cudaMemcpyAsync(scratch[c], u[c], bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+      HalfStep<T> none;
+      memset(&none, 0, sizeof(none));
+      if ((rc = run_row(false, true, none, none))) return rc;
+      if (ndim >= 2 && (rc = run_str(1, 0))) return rc;
+      if (ndim == 3 && (rc = run_str(2, 0))) return rc;
+      const double sc = 1.0 / ((double)nspatial * (double)nspatial);
+      for (int c = 0; c < M; ++c) {
+        density_kernel<T><<<blocks, threads, 0, stream>>>(u[c], obs_dev + c * nspatial, nspatial, nbatch, sc);
+        ++launches;
+        GGP_CUDA(cudaMemcpyAsync(u[c], scratch[c], bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+      count = (size_t)(nspatial * M);
+    } else {
+      return fail(GGP_ERR_INVALID, "unknown observable kind");
+    }
+    GGP_CUDA(cudaGetLastError());
+#ifdef GGP_WITH_NCCL
+    if (comm && nranks > 1) {
+      ncclResult_t r = ncclAllReduce(obs_dev, obs_dev, count, ncclDouble, ncclSum, comm, stream);
+      if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+#endif
+    GGP_CUDA(cudaMemcpyAsync(out, obs_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+
+}  // namespace ggp
+
+struct ggp_plan {
+  ggp::PlanBase* impl;
+};
+
+using namespace ggp;
+
+extern "C" {
+
+int ggp_version(void) { return 100; }
+
+int ggp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* ggp_last_error(void) { return g_err.c_str(); }
+
+int ggp_plan_create(const ggp_desc* d, ggp_plan** out) {
+  if (!d || !out) return fail(GGP_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->abi_version != GGP_ABI_VERSION) return fail(GGP_ERR_INVALID, "abi_version mismatch");
+  if (d->struct_size != sizeof(ggp_desc)) return fail(GGP_ERR_INVALID, "struct_size mismatch");
+  if (d->ndim < 1 || d->ndim > 3) return fail(GGP_ERR_INVALID, "ndim must be 1..3");
+  if (d->ncomp < 1 || d->ncomp > 2) return fail(GGP_ERR_UNSUPPORTED, "ncomp must be 1 or 2");
+  if (d->nbatch < 1) return fail(GGP_ERR_INVALID, "nbatch must be >= 1");
+  for (int i = 0; i < d->ndim; ++i)
+    if (d->n[i] < 1) return fail(GGP_ERR_INVALID, "n[i] must be >= 1");
+  if (d->precision != GGP_C64 && d->precision != GGP_C128) return fail(GGP_ERR_INVALID, "bad precision");
+  if (!(d->dt == d->dt)) return fail(GGP_ERR_INVALID, "dt is NaN");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(GGP_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+  }
+  int dev = d->device;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(GGP_ERR_CUDA, "cudaGetDevice failed");
+  }
+  if (dev >= ndev) return fail(GGP_ERR_INVALID, "device ordinal out of range");
+  GGP_CUDA(cudaSetDevice(dev));
+  PlanBase* impl = d->precision == GGP_C64 ? (PlanBase*)new PlanT<float>() : (PlanBase*)new PlanT<double>();
+  impl->device = dev;
+  int rc = impl->create(*d);
+  if (rc) {
+    delete impl;
+    return rc;
+  }
+  *out = new ggp_plan{impl};
+  return 0;
+}
+
+int ggp_plan_destroy(ggp_plan* p) {
+  if (!p) return 0;
+  delete p->impl;
+  delete p;
+  return 0;
+}
+
+#define GGP_ENTER(p)                                        \
+  if (!(p) || !(p)->impl) return fail(GGP_ERR_INVALID, "null plan"); \
+  GGP_CUDA(cudaSetDevice((p)->impl->device));
+
+int ggp_set_state(ggp_plan* p, const void* const* u) {
+  GGP_ENTER(p);
+  if (!u) return fail(GGP_ERR_INVALID, "null state");
+  return p->impl->set_state(u);
+}
+int ggp_get_state(ggp_plan* p, void* const* u) {
+  GGP_ENTER(p);
+  if (!u) return fail(GGP_ERR_INVALID, "null state");
+  return p->impl->get_state(u);
+}
+int ggp_step(ggp_plan* p, int64_t nsteps, const double* amp, const void* const* noise) {
+  GGP_ENTER(p);
+  return p->impl->step(nsteps, amp, noise);
+}
+int ggp_synchronize(ggp_plan* p) {
+  GGP_ENTER(p);
+  GGP_CUDA(cudaStreamSynchronize(p->impl->stream));
+  return 0;
+}
+int ggp_observe(ggp_plan* p, int kind, double* out) {
+  GGP_ENTER(p);
+  if (!out) return fail(GGP_ERR_INVALID, "null output");
+  return p->impl->observe(kind, out);
+}
+
+int ggp_comm_unique_id(void* id) {
+#ifdef GGP_WITH_NCCL
+  ncclUniqueId uid;
+  ncclResult_t r = ncclGetUniqueId(&uid);
+  if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+  static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id, &uid, 128);
+  return 0;
+#else
+  (void)id;
+  return fail(GGP_ERR_NCCL, "libggp was built without NCCL");
+#endif
+}
+int ggp_comm_init(ggp_plan* p, int nranks, int rank, const void* id) {
+  GGP_ENTER(p);
+#ifdef GGP_WITH_NCCL
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t r = ncclCommInitRank(&p->impl->comm, nranks, uid, rank);
+  if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+  p->impl->nranks = nranks;
+  return 0;
+#else
+  (void)nranks; (void)rank; (void)id;
+  return fail(GGP_ERR_NCCL, "libggp was built without NCCL");
+#endif
+}
+
+void* ggp_state_device_ptr(ggp_plan* p, int c) { return (p && p->impl) ? p->impl->state_ptr(c) : nullptr; }
+
+int ggp_timer_begin(ggp_plan* p) {
+  GGP_ENTER(p);
+  GGP_CUDA(cudaEventRecord(p->impl->ev0, p->impl->stream));
+  return 0;
+}
+int ggp_timer_end(ggp_plan* p, float* ms) {
+  GGP_ENTER(p);
+  GGP_CUDA(cudaEventRecord(p->impl->ev1, p->impl->stream));
+  GGP_CUDA(cudaEventSynchronize(p->impl->ev1));
+  GGP_CUDA(cudaEventElapsedTime(ms, p->impl->ev0, p->impl->ev1));
+  return 0;
+}
+int64_t ggp_launch_count(ggp_plan* p) { return (p && p->impl) ? p->impl->launches : -1; }
+int64_t ggp_device_bytes(ggp_plan* p) { return (p && p->impl) ? p->impl->dev_bytes : -1; }
+
+void* ggp_host_alloc(uint64_t bytes) {
+  void* q = nullptr;
+  if (cudaMallocHost(&q, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    g_err = "cudaMallocHost failed";
+    return nullptr;
+  }
+  return q;
+}
+int ggp_host_free(void* q) {
+  if (q) GGP_CUDA(cudaFreeHost(q));
+  return 0;
+}
+
+int ggp_profile_enable(ggp_plan* p, int on) {
+  GGP_ENTER(p);
+  p->impl->profiling = on != 0;
+  if (on) {
+    for (int i = 0; i < KC_COUNT; ++i) {
+      p->impl->prof_ms[i] = 0;
+      p->impl->prof_n[i] = 0;
+    }
+  }
+  return 0;
+}
+int ggp_profile_read(ggp_plan* p, double* ms_total, int64_t* launches) {
+  GGP_ENTER(p);
+  int rc = p->impl->prof_collect();
+  if (rc) return rc;
+  for (int i = 0; i < KC_COUNT; ++i) {
+    ms_total[i] = p->impl->prof_ms[i];
+    launches[i] = p->impl->prof_n[i];
+  }
+  return 0;
+}
+
+}  // extern "C"

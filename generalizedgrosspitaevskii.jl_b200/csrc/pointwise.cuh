@@ -1,0 +1,185 @@
+// The fused real-space half-step of the reference's muladd_kernel! (src/kernels.jl:37-54), for the
+// registered forms:
+//   u_i <- sum_j E_ij (u_j + (dt/2) a_now S_j) + (dt/2) a_next S_i - i sqrt(dt) eta_i xi_i
+//   E    = cis(-dt G(u)) (x) exp_V[r],   G_i = c_i + sum_j g_ij |u_j|^2   evaluated on the PRE-update field
+// and the k-space multiply  u~ <- exp_D[k] (x) u~  (src/strang_splitting.jl:73-74).
+// `dt` here is the half-step (reference passes dt/2, src/strang_splitting.jl:87,89).
+#pragma once
+#include "cplx.cuh"
+
+namespace ggp {
+
+enum { KIND_NONE = 0, KIND_SCALAR = 1, KIND_DIAG = 2, KIND_FULL = 3 };
+enum { NOISE_OFF = 0, NOISE_HOST = 1, NOISE_PHILOX = 2 };
+
+// per-half-step scalars
+template <typename T>
+struct HalfStep {
+  cpx<T> fnow;    // (dt/2) * a_now   (src/kernels.jl:46)
+  cpx<T> fnext;   // (dt/2) * a_next  (src/kernels.jl:45)
+  const void* xi[2];  // host-fed noise (test mode), one array per component
+  uint32_t ctr;   // global half-step counter (Philox)
+  int apply;      // 0: skip this half-step
+};
+
+template <typename T>
+struct PointwiseParams {
+  T dt;        // half step
+  T sqrt_dt;   // sqrt(half step)
+  const cpx<T>* expV[4];
+  const cpx<T>* S[2];
+  int vkind;   // KIND_*
+  int pump;    // 0 none, 1 scalar broadcast (S[0] for every component), 2 per component
+  int nl;      // 0 none, 1 real coefficients, 2 complex coefficients
+  T nl_c_re[2], nl_c_im[2];
+  T nl_g_re[2][2], nl_g_im[2][2];
+  int noise;   // NOISE_*
+  int noise_real;
+  cpx<T> eta[2];
+  uint32_t seed_lo, seed_hi;
+  long long elem_offset;  // global element index of this plan's element 0 (batch_offset * nspatial)
+};
+
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float exp_t(float a) { return expf(a); }
+__device__ __forceinline__ double exp_t(double a) { return exp(a); }
+
+// Philox4x32-10 (Salmon et al., SC'11), counter = (element index lo, hi, half-step, component).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// xi with <|xi|^2> = 1 (complex prototype) or <xi^2> = 1 (real prototype), Box-Muller in fp32.
+template <typename T>
+__device__ __forceinline__ cpx<T> philox_normal(long long gidx, uint32_t ctr, int comp, uint32_t k0, uint32_t k1,
+                                                int real_proto) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), ctr,
+                                           (uint32_t)comp), k0, k1);
+  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+  const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  const float l = -logf(u1);
+  if (real_proto) {
+    const float rad = sqrtf(2.0f * l);
+    return mk<T>((T)(rad * c), (T)0);
+  }
+  const float rad = sqrtf(l);
+  return mk<T>((T)(rad * c), (T)(rad * s));
+}
+
+// One real-space half-step at one grid point.  sidx: index into the spatial tables; gidx: local
+// element index (spatial + batch) for noise.
+template <typename T, int M>
+__device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseParams<T>& p, const HalfStep<T>& h,
+                                                const long long sidx, const long long gidx) {
+  // nonlinear phase on the pre-update field
+  cpx<T> ph[M];
+  if (p.nl) {
+    T n2[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) n2[j] = cabs2(f[j]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      T gre = p.nl_c_re[i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) gre += p.nl_g_re[i][j] * n2[j];
+      T s, c;
+      sincos_t(-p.dt * gre, &s, &c);
+      ph[i] = mk<T>(c, s);
+      if (p.nl == 2) {
+        T gim = p.nl_c_im[i];
+#pragma unroll
+        for (int j = 0; j < M; ++j) gim += p.nl_g_im[i][j] * n2[j];
+        ph[i] = cscale(ph[i], exp_t(p.dt * gim));
+      }
+    }
+  }
+  // w = f + (dt/2) a_now S
+  cpx<T> w[M], sv[M];
+  if (p.pump) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      sv[j] = p.S[p.pump == 1 ? 0 : j][sidx];
+      w[j] = f[j] + cmul(h.fnow, sv[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < M; ++j) w[j] = f[j];
+  }
+  // res = E w
+  cpx<T> res[M];
+  if (p.vkind == KIND_FULL) {
+    // only a scalar-returning nonlinearity (ph[0] == ph[i]) or none can meet a full V (src/kernels.jl:9)
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      cpx<T> acc = mk<T>((T)0, (T)0);
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc = acc + cmul(p.expV[j * M + i][sidx], w[j]);
+      res[i] = p.nl ? cmul(ph[0], acc) : acc;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      cpx<T> e = w[i];
+      if (p.vkind == KIND_SCALAR) e = cmul(p.expV[0][sidx], e);
+      if (p.vkind == KIND_DIAG) e = cmul(p.expV[i][sidx], e);
+      res[i] = p.nl ? cmul(ph[i], e) : e;
+    }
+  }
+  if (p.pump) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, sv[i]);
+  }
+  if (p.noise) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      cpx<T> xi;
+      if (p.noise == NOISE_HOST) {
+        xi = p.noise_real ? mk<T>(((const T*)h.xi[i])[gidx], (T)0) : ((const cpx<T>*)h.xi[i])[gidx];
+      } else {
+        xi = philox_normal<T>(gidx + p.elem_offset, h.ctr, i, p.seed_lo, p.seed_hi, p.noise_real);
+      }
+      // -i sqrt(dt) eta xi
+      const cpx<T> ex = cmul(p.eta[i], xi);
+      res[i] = res[i] + mk<T>(p.sqrt_dt * ex.y, -p.sqrt_dt * ex.x);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) f[i] = res[i];
+}
+
+// k-space multiply at one point: f <- D[k] (x) f.   planes: [col*M + row] for FULL.
+template <typename T, int M>
+__device__ __forceinline__ void disp_point(cpx<T> (&f)[M], const cpx<T>* const* D, const int kind, const long long idx) {
+  if (kind == KIND_SCALAR) {
+    const cpx<T> d = D[0][idx];
+#pragma unroll
+    for (int i = 0; i < M; ++i) f[i] = cmul(d, f[i]);
+  } else if (kind == KIND_DIAG) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) f[i] = cmul(D[i][idx], f[i]);
+  } else if (kind == KIND_FULL) {
+    cpx<T> r[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      cpx<T> acc = mk<T>((T)0, (T)0);
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc = acc + cmul(D[j * M + i][idx], f[j]);
+      r[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) f[i] = r[i];
+  }
+}
+
+}  // namespace ggp

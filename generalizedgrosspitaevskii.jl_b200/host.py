@@ -1,0 +1,618 @@
+"""Host side of the B200 backend: the reference's user surface
+(`GrossPitaevskiiProblem`, `StrangSplitting`, `init`, `step!`, `solve!`, `solve`) above the C ABI.
+
+It mirrors, in Python, exactly what the Julia shim in `julia/` does (there is no Julia in this
+image): everything that involves the user's closures stays on the host --
+
+  * grids                              src/problem.jl:129-139
+  * resolve_fixed_timestepping         src/fixed_time_stepping.jl:14-24
+  * exp tables via get_exponential     src/misc.jl:12-20   (arbitrary closures, exact parity)
+  * closure recognition: nonlinearity -> c_i + sum_j g_ij |u_j|^2, pump -> S(r) a(t), noise -> const
+    (SURVEY §8a registered forms); an unrecognised closure raises -- there is NO CPU fallback
+  * the pump-amplitude schedule at the reference's (one-dt-late) times, SURVEY Q1
+  * `ts` accumulation and the save loop  src/fixed_time_stepping.jl:38-50
+
+and every grid-sized floating-point operation of the time loop runs in libggp.so.
+
+Array convention (as in oracle/): Julia (n1, ..., nd, batch...) column-major == NumPy C-order
+(batch..., nd, ..., n1).  Closures get coordinates in Julia order (`ks[0]` along n1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+# ------------------------------------------------------------------------------------------------
+# StaticArrays stand-ins and the identity singletons of src/kernels.jl:1-7
+# ------------------------------------------------------------------------------------------------
+
+
+class SVector:
+    def __init__(self, *items):
+        if len(items) == 1 and isinstance(items[0], (list, tuple)):
+            items = tuple(items[0])
+        self.items = list(items)
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+    def __iter__(self):
+        return iter(self.items)
+
+    def _map(self, o, op):
+        if isinstance(o, SVector):
+            return SVector([op(a, b) for a, b in zip(self.items, o.items)])
+        return SVector([op(a, o) for a in self.items])
+
+    def __mul__(self, o):
+        return self._map(o, lambda a, b: a * b)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self._map(o, lambda a, b: a / b)
+
+    def __add__(self, o):
+        return self._map(o, lambda a, b: a + b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._map(o, lambda a, b: a - b)
+
+    def __neg__(self):
+        return SVector([-a for a in self.items])
+
+
+class SMatrix:
+    def __init__(self, rows):
+        self.rows = [list(r) for r in rows]
+        assert all(len(r) == len(self.rows) for r in self.rows), "square matrices only"
+
+    @property
+    def n(self):
+        return len(self.rows)
+
+    def __getitem__(self, ij):
+        return self.rows[ij[0]][ij[1]]
+
+
+def abs2(x):
+    if isinstance(x, SVector):
+        return SVector([abs2(a) for a in x.items])
+    if isinstance(x, (tuple, list)):
+        return SVector([abs2(a) for a in x])
+    x = np.asarray(x)
+    return x.real * x.real + x.imag * x.imag
+
+
+class _Identity:
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        return self
+
+    def __repr__(self):
+        return self._name
+
+
+additiveIdentity = _Identity("additiveIdentity")
+multiplicativeIdentity = _Identity("multiplicativeIdentity")
+
+
+def _absent(f):
+    return f is None or f is additiveIdentity
+
+
+class UnsupportedForm(ValueError):
+    """A closure that is legal in the reference but outside the registered device forms."""
+
+
+# ------------------------------------------------------------------------------------------------
+# problem, grids, time stepping
+# ------------------------------------------------------------------------------------------------
+
+
+def _jl(x):
+    """Julia literal semantics for bare Python numbers (Float64 / Int are strong types)."""
+    if isinstance(x, (np.floating, np.integer)):
+        return x
+    if isinstance(x, (int,)):
+        return int(x)
+    return np.float64(x)
+
+
+class GrossPitaevskiiProblem:
+    """src/problem.jl:97-122."""
+
+    def __init__(self, u0, lengths, *, dispersion=additiveIdentity, potential=additiveIdentity,
+                 nonlinearity=additiveIdentity, pump=additiveIdentity, position_noise_func=additiveIdentity,
+                 momentum_noise_func=additiveIdentity, noise_prototype=additiveIdentity, param=None):
+        u0 = tuple(np.asarray(x) for x in u0)
+        lengths = tuple(lengths)
+        assert all(x.ndim >= len(lengths) for x in u0)      # src/problem.jl:112
+        assert all(x.shape == u0[0].shape for x in u0)      # src/problem.jl:113
+
+        def cplx(x):                                        # complex.(u0), src/problem.jl:114
+            if np.iscomplexobj(x):
+                return x
+            return x.astype(np.complex64 if x.dtype == np.float32 else np.complex128)
+
+        self.u0 = tuple(cplx(x) for x in u0)
+        ls = [_jl(l) for l in lengths]
+        lt = np.result_type(*[np.asarray(l).dtype for l in ls])
+        self.lengths = tuple(lt.type(l) for l in ls)        # promote(lengths...), :115
+        self.dispersion, self.potential = dispersion, potential
+        self.nonlinearity, self.pump = nonlinearity, pump
+        self.position_noise_func, self.momentum_noise_func = position_noise_func, momentum_noise_func
+        self.noise_prototype = noise_prototype
+        self.param = param
+
+    def __repr__(self):
+        return f"{len(self.lengths)}D GrossPitaevskiiProblem"
+
+    @property
+    def ndim(self):
+        return len(self.lengths)
+
+    @property
+    def sizes(self):
+        s = self.u0[0].shape
+        return tuple(reversed(s[len(s) - self.ndim:]))      # (n1, ..., nd)
+
+
+def direct_grid(prob):
+    """src/problem.jl:129-133: x_j = (j-1) L/N."""
+    out = []
+    for Lk, n in zip(prob.lengths, prob.sizes):
+        step = Lk / n if isinstance(Lk, np.floating) else np.float64(Lk) / n
+        out.append(np.arange(n).astype(np.asarray(step).dtype) * step)
+    return tuple(out)
+
+
+def reciprocal_grid(prob):
+    """src/problem.jl:135-139 with AbstractFFTs.fftfreq (negative Nyquist bin)."""
+    out = []
+    for Lk, n in zip(prob.lengths, prob.sizes):
+        ratio = n / Lk if isinstance(Lk, np.floating) else np.float64(n) / np.float64(Lk)
+        ft = np.asarray(ratio).dtype
+        fs = ft.type(2 * math.pi) * ft.type(n) / ft.type(Lk)
+        i = np.arange(n)
+        idx = np.where(i < ((n + 1) >> 1), i, i - n).astype(ft)
+        out.append(idx * (fs / ft.type(n)))
+    return tuple(out)
+
+
+def _mesh(axes):
+    d = len(axes)
+    pts = []
+    for m, ax in enumerate(axes):
+        shape = [1] * d
+        shape[d - 1 - m] = len(ax)
+        pts.append(ax.reshape(shape))
+    return tuple(pts)
+
+
+def resolve_fixed_timestepping(dt, tspan, nsaves):
+    """src/fixed_time_stepping.jl:14-24 (dt is rewritten)."""
+    dt = _jl(dt)
+    t0, t1 = _jl(tspan[0]), _jl(tspan[-1])
+    T = np.result_type(*[np.asarray(v).dtype for v in (dt, t0, t1)])
+    if not np.issubdtype(T, np.floating):
+        T = np.dtype(np.float64)
+    ts = np.empty(nsaves + 1, dtype=T)
+    ts[0] = t0
+    dT = T.type(T.type(t1) - T.type(t0)) / nsaves
+    steps_per_save = int(math.ceil(dT / dt))
+    return dT / steps_per_save, ts, steps_per_save
+
+
+class StrangSplitting:
+    """src/strang_splitting.jl:7."""
+
+
+# ------------------------------------------------------------------------------------------------
+# tables: get_exponential (src/misc.jl:12-20), evaluated on the host with the user's closure
+# ------------------------------------------------------------------------------------------------
+
+
+def _cis(z):
+    z = np.asarray(z)
+    if np.iscomplexobj(z):
+        return np.exp(-z.imag) * (np.cos(z.real) + 1j * np.sin(z.real))
+    return np.cos(z) + 1j * np.sin(z)
+
+
+def _expm2(a, c, b, d):
+    """exp of [[a, b], [c, d]] per grid point: the closed form StaticArrays uses for 2x2
+    (sqrt of the discriminant, two expm1, series branch for a vanishing discriminant)."""
+    a, b, c, d = np.broadcast_arrays(*(np.asarray(v, dtype=np.result_type(a, b, c, d, np.complex64))
+                                       for v in (a, b, c, d)))
+    z = np.sqrt((a - d) * (a - d) + 4 * b * c)
+    e = np.expm1((a + d - z) / 2)
+    f = np.expm1((a + d + z) / 2)
+    eps = np.finfo(z.real.dtype).eps
+    tiny = (z.real ** 2 + z.imag ** 2) < eps * eps
+    g = np.where(tiny, np.exp((a + d) / 2) * (1 + z * z / 24), (f - e) / np.where(tiny, 1, z))
+    return (g * (a - d) + f + e) / 2 + 1, g * c, g * b, (-g * (a - d) + f + e) / 2 + 1  # m11 m21 m12 m22
+
+
+def exp_table(f, grid, param, dt, M):
+    """Returns (kind, AoS array of shape (npoints, ncols) complex) for cis(-dt * f(point, param))."""
+    if _absent(f):
+        return L.TABLE_NONE, None
+    shape = tuple(len(g) for g in reversed(grid))
+    val = f(_mesh(grid), param)
+    if isinstance(val, SMatrix) and val.n == 1:
+        val = val[0, 0] if M == 1 else val
+    if isinstance(val, SVector) and len(val) == 1 and M == 1:
+        val = val[0]
+    if isinstance(val, SVector):
+        if len(val) != M:
+            raise ValueError("SVector table length must equal the number of components")
+        cols = [np.broadcast_to(_cis(-dt * np.asarray(v)), shape) for v in val]
+        kind = L.TABLE_DIAG
+    elif isinstance(val, SMatrix):
+        if val.n != M or M != 2:
+            raise UnsupportedForm("matrix-valued tables are supported for 2x2 (M = 2) only")
+        m11, m21, m12, m22 = _expm2(*(1j * (-dt * np.asarray(val[i, j])) for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))))
+        cols = [np.broadcast_to(m, shape) for m in (m11, m21, m12, m22)]  # column-major like SMatrix
+        kind = L.TABLE_FULL
+    else:
+        cols = [np.broadcast_to(_cis(-dt * np.asarray(val)), shape)]
+        kind = L.TABLE_SCALAR
+    table = np.stack([np.asarray(c).reshape(-1) for c in cols], axis=1)
+    return kind, np.ascontiguousarray(table)
+
+
+# ------------------------------------------------------------------------------------------------
+# closure recognition (registered forms)
+# ------------------------------------------------------------------------------------------------
+
+
+def recognise_nonlinearity(f, param, M, rng=None):
+    """Fit G_i(u) = c_i + sum_j g_ij |u_j|^2 by probing the closure; verify on held-out samples.
+    Returns (scalar_flag, c[M] complex, g[M][M] complex)."""
+    rng = rng or np.random.default_rng(0xC0FFEE)
+    P = 4 * (M + 1) + 8
+
+    def probe(n):
+        amp = rng.uniform(0.2, 2.0, size=(M, n))
+        ph = np.exp(2j * np.pi * rng.uniform(size=(M, n)))
+        return amp * ph
+
+    def evaluate(u):
+        val = f(SVector([u[j] for j in range(M)]), param)
+        scalar = True
+        if isinstance(val, SMatrix):
+            if val.n != 1:
+                raise UnsupportedForm("matrix-valued nonlinearity (docs general_overview.md:77) is not a registered form")
+            val = SVector(val[0, 0])
+        if isinstance(val, SVector):
+            scalar = False
+            if len(val) == 1 and isinstance(val[0], SVector):
+                val = val[0]
+            rows = [np.broadcast_to(np.asarray(v, dtype=complex), u.shape[1:]) for v in val]
+        else:
+            rows = [np.broadcast_to(np.asarray(val, dtype=complex), u.shape[1:])]
+        return scalar, np.stack(rows)
+
+    u = probe(P)
+    scalar, G = evaluate(u)
+    if not scalar and G.shape[0] != M:
+        raise UnsupportedForm("nonlinearity must return a Number or an SVector of length M")
+    A = np.concatenate([np.ones((1, P)), np.abs(u) ** 2], axis=0).T        # (P, M+1)
+    coef, *_ = np.linalg.lstsq(A, G.T, rcond=None)                          # (M+1, rows)
+    v = probe(16)
+    _, Gv = evaluate(v)
+    pred = (np.concatenate([np.ones((1, 16)), np.abs(v) ** 2], axis=0).T @ coef).T
+    scale = max(1e-300, np.abs(Gv).max(), np.abs(coef).max())
+    if np.abs(pred - Gv).max() > 1e-9 * scale:
+        raise UnsupportedForm("nonlinearity is not of the registered form c_i + sum_j g_ij |u_j|^2 "
+                              "(the B200 backend has no CPU fallback)")
+    rows = G.shape[0]
+    c = np.zeros(M, dtype=complex)
+    g = np.zeros((M, M), dtype=complex)
+    for i in range(M):
+        src = 0 if rows == 1 else i
+        c[i] = coef[0, src]
+        g[i, :] = coef[1:, src]
+    # clean round-off of the fit
+    c[np.abs(c) < 1e-13 * scale] = 0
+    g[np.abs(g) < 1e-13 * scale] = 0
+    return scalar or rows == 1 and M == 1, c, g
+
+
+class PumpModel:
+    """F_i(r, t) = S_i(r) a(t): S table (npoints, ncomp) and an amplitude function a(t)."""
+
+    def __init__(self, f, prob, tspan, times):
+        grid = direct_grid(prob)
+        pts = _mesh(grid)
+        shape = tuple(len(g) for g in reversed(grid))
+        self.f, self.param, self.M = f, prob.param, len(prob.u0)
+
+        def on_grid(t):
+            val = f(pts, prob.param, t)
+            if isinstance(val, SMatrix):
+                if val.n != 1:
+                    raise UnsupportedForm("matrix-valued pump")
+                val = SVector(val[0, 0])
+            if isinstance(val, SVector):
+                cols = [np.broadcast_to(np.asarray(v, dtype=complex), shape).reshape(-1) for v in val]
+            else:
+                cols = [np.broadcast_to(np.asarray(val, dtype=complex), shape).reshape(-1)]
+            return np.stack(cols, axis=1)
+
+        cand = [tspan[0], tspan[-1], 0.5 * (tspan[0] + tspan[-1])]
+        if len(times):
+            cand += [times[0], times[len(times) // 3], times[2 * len(times) // 3]]
+        best, tref = None, None
+        for t in cand:
+            F = on_grid(t)
+            if best is None or np.abs(F).max() > np.abs(best).max():
+                best, tref = F, t
+        self.ncomp = best.shape[1]
+        if self.ncomp not in (1, self.M):
+            raise UnsupportedForm("pump must return a Number or an SVector of length M")
+        self.zero = np.abs(best).max() == 0
+        flat = np.abs(best).argmax()
+        self.pidx, self.cidx = np.unravel_index(flat, best.shape)
+        self.S = best.copy()                      # a(tref) == 1 by construction
+        self.tref = tref
+        # coordinates of the probe point
+        multi = np.unravel_index(self.pidx, shape)            # (i_d, ..., i_1)
+        self.rpt = tuple(np.asarray(g[i]).reshape(()) for g, i in zip(grid, reversed(multi)))
+        self._ref = best[self.pidx, self.cidx]
+        # verify separability on the full grid at a few other times
+        if not self.zero:
+            for t in cand[:3] + ([times[len(times) // 2]] if len(times) else []):
+                F = on_grid(t)
+                a = self.amp(t)
+                if np.abs(F - a * self.S).max() > 1e-10 * max(np.abs(F).max(), np.abs(self.S).max()):
+                    raise UnsupportedForm("pump is not separable as S(r) a(t) (dense time-dependent pumps are "
+                                          "not a registered form; the B200 backend has no CPU fallback)")
+
+    def amp(self, t):
+        if self.zero:
+            return 0.0 + 0.0j
+        val = self.f(self.rpt, self.param, t)
+        if isinstance(val, SMatrix):
+            val = SVector(val[0, 0])
+        if isinstance(val, SVector):
+            val = val[self.cidx]
+        return complex(np.asarray(val, dtype=complex).reshape(())) / complex(self._ref)
+
+
+def recognise_noise(f, prob, rng=None):
+    """eta_i = const per component (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29)."""
+    rng = rng or np.random.default_rng(0xBEEF)
+    M = len(prob.u0)
+    grid = direct_grid(prob)
+    vals = []
+    for _ in range(4):
+        u = SVector([complex(rng.standard_normal(), rng.standard_normal()) for _ in range(M)])
+        r = tuple(g[rng.integers(len(g))] for g in grid)
+        v = f(u, r, prob.param)
+        if isinstance(v, SVector):
+            v = [complex(np.asarray(x).reshape(())) for x in v]
+            if len(v) != M:
+                raise UnsupportedForm("noise amplitude SVector must have length M")
+        else:
+            v = [complex(np.asarray(v).reshape(()))] * M
+        vals.append(v)
+    vals = np.array(vals)
+    if np.abs(vals - vals[0]).max() > 1e-12 * max(1e-300, np.abs(vals).max()):
+        raise UnsupportedForm("field- or position-dependent noise amplitudes are not a registered form yet "
+                              "(SURVEY §8f N4); the B200 backend has no CPU fallback")
+    return vals[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# iterator = StrangSplittingIterator (src/strang_splitting.jl:9-67) with a device plan inside
+# ------------------------------------------------------------------------------------------------
+
+
+def _ptr_array(arrs):
+    arr = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+class StrangSplittingIterator:
+    def __init__(self, prob, tspan, *, dt, nsaves, save_start=True, rng=None, device=-1,
+                 batch_offset=0, stream=None):
+        lib = L.load()
+        self.lib = lib
+        self.prob = prob
+        self.dt, self.ts, self.steps_per_save = resolve_fixed_timestepping(dt, tspan, nsaves)
+        self.nsaves, self.save_start = nsaves, bool(save_start)
+        self.tspan = tspan
+        M = len(prob.u0)
+        self.M = M
+        dtype = prob.u0[0].dtype
+        if dtype not in (np.complex64, np.complex128):
+            raise ValueError("fields must be ComplexF32 or ComplexF64")
+        self.dtype = dtype
+        sizes = prob.sizes
+        nspatial = int(np.prod(sizes))
+        self.nbatch = int(prob.u0[0].size // nspatial)
+        self.result = tuple(np.stack([x] * (nsaves + self.save_start), axis=0) for x in prob.u0)  # :41-43
+
+        rg, dg = reciprocal_grid(prob), direct_grid(prob)
+        dkind, dtab = exp_table(prob.dispersion, rg, prob.param, self.dt, M)            # :53
+        vkind, vtab = exp_table(prob.potential, dg, prob.param, self.dt / 2, M)         # :54
+
+        d = L.GgpDesc()
+        d.abi_version, d.struct_size = L.GGP_ABI_VERSION, C.sizeof(L.GgpDesc)
+        d.ndim, d.ncomp = prob.ndim, M
+        for i, n in enumerate(sizes):
+            d.n[i] = int(n)
+        d.nbatch, d.batch_offset = self.nbatch, int(batch_offset)
+        d.precision = L.GGP_C64 if dtype == np.complex64 else L.GGP_C128
+        d.table_precision = L.GGP_C128
+        d.device = device
+        d.stream = stream
+        d.dt = float(self.dt)
+        keep = []
+
+        def as_c128(t):
+            a = np.ascontiguousarray(t, dtype=np.complex128)
+            keep.append(a)
+            return a.ctypes.data
+
+        d.disp_kind, d.pot_kind = dkind, vkind
+        d.disp_table = as_c128(dtab) if dtab is not None else None
+        d.pot_table = as_c128(vtab) if vtab is not None else None
+
+        if not _absent(prob.nonlinearity):
+            scalar, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, M)
+            d.nl_kind, d.nl_scalar = L.NL_DIAG, int(bool(scalar))
+            for i in range(M):
+                d.nl_c[i][0], d.nl_c[i][1] = c[i].real, c[i].imag
+                for j in range(M):
+                    d.nl_g[i][j][0], d.nl_g[i][j][1] = g[i, j].real, g[i, j].imag
+            self.nl = (scalar, c, g)
+
+        # pump amplitude schedule at the reference's times
+        nsteps = nsaves * self.steps_per_save
+        self.pump_model = None
+        self.amps = None
+        if not _absent(prob.pump):
+            t = self.ts[0]
+            times = np.empty((nsteps, 2), dtype=self.ts.dtype)
+            for i in range(nsteps):
+                t = t + self.dt
+                times[i, 0] = t + self.dt / 2
+                times[i, 1] = t + self.dt
+            pm = PumpModel(prob.pump, prob, (self.ts[0], _jl(tspan[-1])), times.reshape(-1))
+            self.pump_model = pm
+            d.pump_kind, d.pump_ncomp = L.PUMP_SEPARABLE, pm.ncomp
+            d.pump_table = as_c128(pm.S)
+            a0 = pm.amp(self.ts[0])                                                     # :58
+            d.pump_amp0[0], d.pump_amp0[1] = a0.real, a0.imag
+            amps = np.array([[pm.amp(times[i, 0]), pm.amp(times[i, 1])] for i in range(nsteps)], dtype=np.complex128)
+            if np.all(amps == a0):
+                self.amps = None            # static pump: the library repeats pump_amp0
+            else:
+                self.amps = np.ascontiguousarray(amps)
+
+        self.noise_real = False
+        if not _absent(prob.position_noise_func):
+            if _absent(prob.noise_prototype):
+                raise ValueError("position_noise_func needs a noise_prototype")
+            eta = recognise_noise(prob.position_noise_func, prob)
+            proto = prob.noise_prototype[0]
+            self.noise_real = not np.iscomplexobj(proto)
+            d.noise_kind, d.noise_real = L.NOISE_CONST, int(self.noise_real)
+            for i in range(M):
+                d.noise_eta[i][0], d.noise_eta[i][1] = eta[i].real, eta[i].imag
+            if rng is None:
+                seed = int.from_bytes(os.urandom(8), "little")
+            elif isinstance(rng, (int, np.integer)):
+                seed = int(rng)
+            else:
+                seed = int(rng.integers(0, 2 ** 63))
+            d.seed = seed & (2 ** 64 - 1)
+            self.seed = d.seed
+
+        self._desc, self._keep = d, keep
+        handle = C.c_void_p()
+        L.check(lib.ggp_plan_create(C.byref(d), C.byref(handle)))
+        self.handle = handle
+        self.u = [np.ascontiguousarray(x).copy() for x in prob.u0]                      # :48
+        L.check(lib.ggp_set_state(self.handle, _ptr_array(self.u)))
+        self._step_index = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ggp_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device stepping ---------------------------------------------------------------------
+    def advance(self, nsteps, noise_buffers=None):
+        """nsteps x step! on the device (src/fixed_time_stepping.jl:43-47)."""
+        amp_ptr = None
+        if self.amps is not None:
+            seg = np.ascontiguousarray(self.amps[self._step_index:self._step_index + nsteps])
+            assert seg.shape[0] == nsteps, "stepping past the end of the pump schedule"
+            amp_ptr = seg.ctypes.data
+        nptr = None
+        if noise_buffers is not None:
+            real_t = np.float32 if self.dtype == np.complex64 else np.float64
+            want = real_t if self.noise_real else self.dtype
+            bufs = [np.ascontiguousarray(b, dtype=want) for b in noise_buffers]
+            assert len(bufs) == 2 * nsteps * self.M, "need 2*nsteps*M noise buffers (step, half-step, component)"
+            nptr = _ptr_array(bufs)
+        L.check(self.lib.ggp_step(self.handle, nsteps, amp_ptr, nptr))
+        self._step_index += nsteps
+
+    def fetch(self):
+        L.check(self.lib.ggp_get_state(self.handle, _ptr_array(self.u)))
+        return self.u
+
+    def observe(self, kind):
+        nspatial = int(np.prod(self.prob.sizes))
+        n = self.M if kind == L.OBS_NORM else self.M * nspatial
+        out = np.empty(n, dtype=np.float64)
+        L.check(self.lib.ggp_observe(self.handle, kind, out.ctypes.data))
+        if kind == L.OBS_NORM:
+            return out
+        return out.reshape((self.M,) + tuple(reversed(self.prob.sizes)))
+
+
+def init(prob, alg, tspan, *, dt, nsaves, show_progress=True, progress=None, save_start=True,
+         workgroup_size=(), rng=None, **backend_kw):
+    """CommonSolve.init (src/strang_splitting.jl:32-39).  `workgroup_size` is accepted and ignored
+    (block sizes are fixed per kernel); `show_progress` / `progress` are host-side cosmetics."""
+    assert isinstance(alg, StrangSplitting)
+    return StrangSplittingIterator(prob, tspan, dt=dt, nsaves=nsaves, save_start=save_start, rng=rng, **backend_kw)
+
+
+def step_(it, t=None, dt=None, noise_buffers=None):
+    """CommonSolve.step! (src/strang_splitting.jl:86-90): one Strang step on the device."""
+    it.advance(1, noise_buffers)
+
+
+def solve_(it, noise_buffers=None):
+    """CommonSolve.solve! (src/fixed_time_stepping.jl:26-54)."""
+    off = 1 if it.save_start else 0
+    t = it.ts[0]
+    sps, M = it.steps_per_save, it.M
+    for n in range(it.nsaves):
+        nb = None
+        if noise_buffers is not None:
+            nb = noise_buffers[n * sps * 2 * M:(n + 1) * sps * 2 * M]
+        it.advance(sps, nb)                                  # :43-47 batched into one call
+        for _ in range(sps):
+            t = t + it.dt                                    # :44 (accumulated in T)
+        u = it.fetch()                                       # :48
+        for r, x in zip(it.result, u):
+            r[n + off] = x
+        it.ts[n + 1] = t                                     # :49
+    return it.ts[1 - off:], it.result                        # :53
+
+
+def solve(prob, alg, tspan, *, noise_buffers=None, **kw):
+    """solve(prob, StrangSplitting(), tspan; dt, nsaves, ...) (src/fixed_time_stepping.jl:79-81)."""
+    it = init(prob, alg, tspan, **kw)
+    try:
+        return solve_(it, noise_buffers)
+    finally:
+        it.close()

@@ -1,0 +1,188 @@
+/*
+ * ggp.h -- C ABI of libggp.so, the B200 (sm_100a) backend for the Strang-splitting time step of
+ * GeneralizedGrossPitaevskii.jl.
+ *
+ * The reference has no FFI today: its backends are reached by Julia multiple dispatch on the array
+ * type (src/strang_splitting.jl:62, src/misc.jl:7,55).  The seam this library sits behind is the
+ * CommonSolve triple `init / step! / solve!` of StrangSplitting:
+ *
+ *   ggp_plan_create   replaces  init(prob, ::StrangSplitting, tspan; ...)   src/strang_splitting.jl:32-67
+ *                     (device state, exp(-i dt D(k)) / exp(-i dt/2 V(r)) tables from
+ *                      get_exponential src/misc.jl:12-20, pump buffers src/misc.jl:22-27,
+ *                      FFT plans src/misc.jl:53-58)
+ *   ggp_set_state     replaces  u = copy.(prob.u0)                         src/strang_splitting.jl:48
+ *   ggp_step          replaces  the inner loop `for _ in 1:steps_per_save; t += dt; step!(iter,t,dt)`
+ *                                                                          src/fixed_time_stepping.jl:43-47
+ *                     i.e. nsteps x step!                                  src/strang_splitting.jl:86-90
+ *                     = potential_pump_step! (:78-84) + diffusion_step! (:69-76) + potential_pump_step!
+ *                     with muladd_kernel! (src/kernels.jl:37-54), perform_ft! (src/misc.jl:60-64),
+ *                     sample_noise! (src/misc.jl:44-51), evaluate_pump! (src/misc.jl:29-42)
+ *   ggp_get_state     replaces  map(copy!, slice, iter.u)                  src/fixed_time_stepping.jl:48
+ *   ggp_observe       (no reference counterpart; on-device ensemble observables)
+ *
+ * Conventions
+ *   - Arrays are Julia column-major: index (i1, ..., id, b) with i1 fastest, batch (trajectory) dims
+ *     flattened into one trailing index b.  One array per field component (the reference's
+ *     NTuple{M,Array}).
+ *   - Every host pointer is BORROWED for the duration of the call only.
+ *   - Every function returns 0 on success or a negative ggp_status; the message is available from
+ *     ggp_last_error() (thread-local).  No C++ exception crosses this boundary.
+ *   - A plan is not thread-safe; distinct plans are independent.  ggp_step is stream-ordered and may
+ *     return before the GPU finishes; ggp_get_state / ggp_observe / ggp_synchronize / destroy block.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     GGP_ERR_CUDA.
+ */
+#ifndef GGP_H
+#define GGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGP_ABI_VERSION 1u
+
+typedef enum ggp_status {
+  GGP_OK = 0,
+  GGP_ERR_INVALID = -1,     /* bad descriptor / argument */
+  GGP_ERR_UNSUPPORTED = -2, /* legal in the reference, not covered by this backend (e.g. non power-of-two n) */
+  GGP_ERR_CUDA = -3,        /* CUDA runtime failure (message in ggp_last_error) */
+  GGP_ERR_NCCL = -4,
+  GGP_ERR_ALLOC = -5
+} ggp_status;
+
+typedef enum ggp_precision { GGP_C64 = 0, GGP_C128 = 1 } ggp_precision;
+
+/* kind of the exp tables: what `dispersion(k,param)` / `potential(r,param)` returned in Julia */
+typedef enum ggp_table_kind {
+  GGP_TABLE_NONE = 0,   /* AdditiveIdentity -> multiplicativeIdentity (src/misc.jl:12) */
+  GGP_TABLE_SCALAR = 1, /* Number: one complex per point */
+  GGP_TABLE_DIAG = 2,   /* SVector{M}: M complex per point (elementwise product, src/kernels.jl:10) */
+  GGP_TABLE_FULL = 3    /* SMatrix{M,M}: M*M complex per point, column-major (m11,m21,m12,m22) */
+} ggp_table_kind;
+
+typedef enum ggp_nl_kind {
+  GGP_NL_NONE = 0,
+  GGP_NL_DIAG = 1 /* G_i(u) = c_i + sum_j g_ij |u_j|^2   (every nonlinearity in test/, examples/, docs/) */
+} ggp_nl_kind;
+
+typedef enum ggp_pump_kind {
+  GGP_PUMP_NONE = 0,
+  GGP_PUMP_SEPARABLE = 1 /* F_i(r,t) = S_i(r) a(t); a static pump is a(t) = const */
+} ggp_pump_kind;
+
+typedef enum ggp_noise_kind {
+  GGP_NOISE_NONE = 0,
+  GGP_NOISE_CONST = 1 /* eta_i(u,r) = const (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29) */
+} ggp_noise_kind;
+
+typedef enum ggp_observable {
+  GGP_OBS_DENSITY = 0,  /* out[c][r] = sum over local trajectories |u_c(r)|^2        (double, M*nspatial) */
+  GGP_OBS_MOMENTUM = 1, /* out[c][k] = sum over local trajectories |fft(u_c)(k)|^2/N^2 (double, M*nspatial) */
+  GGP_OBS_NORM = 2      /* out[c]    = sum over everything |u_c|^2                    (double, M) */
+} ggp_observable;
+
+typedef struct ggp_desc {
+  uint32_t abi_version; /* GGP_ABI_VERSION */
+  uint32_t struct_size; /* sizeof(ggp_desc) as seen by the caller */
+
+  int32_t ndim;         /* number of FFT'd dims, 1..3 (length(lengths)) */
+  int32_t ncomp;        /* M = length(u0), 1 or 2 */
+  int64_t n[3];         /* spatial sizes, n[0] fastest; powers of two */
+  int64_t nbatch;       /* trajectories held by THIS plan (product of trailing dims / shards) */
+  int64_t batch_offset; /* global index of this plan's first trajectory (Philox counters are global,
+                           so results do not depend on the sharding) */
+  int32_t precision;    /* ggp_precision of the fields */
+  int32_t table_precision; /* ggp_precision of disp_table / pot_table / pump_table as passed in */
+  int32_t device;       /* CUDA ordinal, -1 = current device */
+  int32_t reserved0;
+  void *stream;         /* cudaStream_t to run on; NULL = the plan creates its own */
+
+  double dt;            /* the RESOLVED step _dt of resolve_fixed_timestepping (src/fixed_time_stepping.jl:19-21) */
+
+  /* exp_Ddt = cis(-dt*D(k)) on the reciprocal grid, exp_Vdt = cis(-dt/2*V(r)) on the direct grid,
+     exactly as get_exponential builds them (src/strang_splitting.jl:53-54).  Array-of-structs as
+     Julia stores Array{SVector/SMatrix}: point-major, then the static entries column-major. */
+  int32_t disp_kind;    /* ggp_table_kind */
+  int32_t pot_kind;     /* ggp_table_kind */
+  const void *disp_table;
+  const void *pot_table;
+
+  /* nonlinearity, registered form; complex coefficients as (re, im) */
+  int32_t nl_kind;      /* ggp_nl_kind */
+  int32_t nl_scalar;    /* 1: the closure returned a Number (same G for every component; may be combined
+                              with a FULL potential table), 0: SVector */
+  double nl_c[2][2];    /* c_i          [i][re/im] */
+  double nl_g[2][2][2]; /* g_ij         [i][j][re/im] */
+
+  /* pump */
+  int32_t pump_kind;    /* ggp_pump_kind */
+  int32_t pump_ncomp;   /* 1: closure returned a Number (added to every component, src/kernels.jl:17), M: SVector */
+  const void *pump_table; /* S(r): complex, point-major then component */
+  double pump_amp0[2];  /* a(tspan[1]) -- the value primed by evaluate_pump! at init (src/strang_splitting.jl:58) */
+
+  /* position noise: noise = -i*sqrt(dt/2) * eta_i * xi   (src/kernels.jl:42) */
+  int32_t noise_kind;   /* ggp_noise_kind */
+  int32_t noise_real;   /* 1: noise_prototype is a real array (xi ~ N(0,1)); 0: complex (<|xi|^2> = 1) */
+  double noise_eta[2][2]; /* eta_i [i][re/im]; if the closure returned a Number, repeat it */
+  uint64_t seed;        /* Philox4x32-10 key */
+} ggp_desc;
+
+typedef struct ggp_plan ggp_plan;
+
+int ggp_version(void);
+int ggp_device_count(void);
+const char *ggp_last_error(void);
+
+int ggp_plan_create(const ggp_desc *desc, ggp_plan **out);
+int ggp_plan_destroy(ggp_plan *plan);
+
+/* u_host: M pointers to host arrays of nspatial*nbatch complex numbers of the plan's precision */
+int ggp_set_state(ggp_plan *plan, const void *const *u_host);
+int ggp_get_state(ggp_plan *plan, void *const *u_host);
+
+/*
+ * Advance nsteps Strang steps.
+ *   pump_amp  : NULL (static pump: a(t) = pump_amp0), or 2*nsteps complex doubles (re,im): for step s the
+ *               values a(t_s + dt/2), a(t_s + dt) where t_s is the reference's already-incremented t
+ *               (src/fixed_time_stepping.jl:44-45, src/strang_splitting.jl:87,89).
+ *               The library keeps the previous value (F_now) across calls.
+ *   noise_host: NULL => in-kernel Philox stream; otherwise TEST MODE: 2*nsteps*M pointers to host arrays
+ *               (same shape as the state; complex of the plan's precision, or real if noise_real) in the
+ *               reference's draw order: step, half-step, component (src/misc.jl:44-51).
+ */
+int ggp_step(ggp_plan *plan, int64_t nsteps, const double *pump_amp, const void *const *noise_host);
+
+int ggp_synchronize(ggp_plan *plan);
+
+/* Ensemble observables summed over this plan's trajectories, written as doubles to out_host.
+   If a communicator was attached with ggp_comm_init the sums are all-reduced over ranks (NCCL). */
+int ggp_observe(ggp_plan *plan, int kind, double *out_host);
+
+/* Multi-GPU (one process per GPU).  unique_id: the 128-byte ncclUniqueId produced by
+   ggp_comm_unique_id on rank 0 and broadcast by the caller's own plumbing. */
+int ggp_comm_unique_id(void *unique_id_128);
+int ggp_comm_init(ggp_plan *plan, int nranks, int rank, const void *unique_id_128);
+
+/* Harness helpers (bench / tests): device pointers, device-side timing on the plan's stream,
+   pinned host memory, and the number of kernels launched so far. */
+void *ggp_state_device_ptr(ggp_plan *plan, int comp);
+int ggp_timer_begin(ggp_plan *plan);
+int ggp_timer_end(ggp_plan *plan, float *milliseconds);
+int64_t ggp_launch_count(ggp_plan *plan);
+void *ggp_host_alloc(uint64_t bytes);
+int ggp_host_free(void *p);
+/* bytes of device memory the plan owns */
+int64_t ggp_device_bytes(ggp_plan *plan);
+/* Per-kernel-class device timing inside ggp_step (CUDA events around every launch on the plan's
+   stream).  Classes: 0 = contiguous-axis kernel (inverse FFT_x + real-space half-steps + forward
+   FFT_x), 1 = strided kernel with the dispersion multiply, 2 = strided forward-only / inverse-only
+   (3-D middle axis), 3 = 1-D whole-step kernel.  ms_total / launches: arrays of 4. */
+int ggp_profile_enable(ggp_plan *plan, int on);
+int ggp_profile_read(ggp_plan *plan, double *ms_total, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGP_H */
