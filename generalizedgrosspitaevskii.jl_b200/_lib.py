@@ -21,7 +21,7 @@ EXPORTS = [
     "ggp_set_state", "ggp_get_state", "ggp_step", "ggp_synchronize", "ggp_observe",
     "ggp_comm_unique_id", "ggp_comm_init", "ggp_state_device_ptr", "ggp_timer_begin", "ggp_timer_end",
     "ggp_launch_count", "ggp_host_alloc", "ggp_host_free", "ggp_device_bytes", "ggp_profile_enable",
-    "ggp_profile_read",
+    "ggp_profile_read", "ggp_debug_l2_flush",
 ]
 
 
@@ -90,6 +90,7 @@ def load():
     lib.ggp_host_alloc.restype = vp
     lib.ggp_host_free.argtypes = [vp]
     lib.ggp_profile_enable.argtypes = [vp, C.c_int]
+    lib.ggp_debug_l2_flush.argtypes = [vp, C.c_uint64]
     lib.ggp_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     _lib = lib
     return lib

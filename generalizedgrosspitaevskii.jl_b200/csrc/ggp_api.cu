@@ -141,6 +141,9 @@ struct PlanBase {
   ncclComm_t comm = nullptr;
 #endif
   int nranks = 1;
+  // measurement aid: evict L2 after every kernel (timing hygiene for working sets smaller than L2)
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
 
   int prof_begin(int cls) {
     if (!profiling) return 0;
@@ -154,8 +157,8 @@ struct PlanBase {
     return 0;
   }
   int prof_end() {
-    if (!profiling) return 0;
-    GGP_CUDA(cudaEventRecord(pev.back(), stream));
+    if (profiling) GGP_CUDA(cudaEventRecord(pev.back(), stream));
+    if (flush_buf) GGP_CUDA(cudaMemsetAsync(flush_buf, 0, flush_bytes, stream));
     return 0;
   }
   int prof_collect() {
@@ -202,6 +205,7 @@ struct PlanT : PlanBase {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : allocs) cudaFree(p);
+    if (flush_buf) cudaFree(flush_buf);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (cudaEvent_t e : pev) cudaEventDestroy(e);
@@ -741,6 +745,21 @@ void* ggp_host_alloc(uint64_t bytes) {
 }
 int ggp_host_free(void* q) {
   if (q) GGP_CUDA(cudaFreeHost(q));
+  return 0;
+}
+
+int ggp_debug_l2_flush(ggp_plan* p, uint64_t bytes) {
+  GGP_ENTER(p);
+  GGP_CUDA(cudaStreamSynchronize(p->impl->stream));
+  if (p->impl->flush_buf) {
+    cudaFree(p->impl->flush_buf);
+    p->impl->flush_buf = nullptr;
+    p->impl->flush_bytes = 0;
+  }
+  if (bytes) {
+    GGP_CUDA(cudaMalloc(&p->impl->flush_buf, bytes));
+    p->impl->flush_bytes = bytes;
+  }
   return 0;
 }
 

@@ -1,0 +1,29 @@
+"""One gpurun call: headline bench, ncu launch list, ncu --set full of the two hot kernels.
+Usage on the GPU box (repo root):  python profile_round.py <tag> [bench args...]"""
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+extra = sys.argv[2:]
+os.makedirs("gpurun_out", exist_ok=True)
+
+
+def sh(cmd, timeout=None):
+    print("+", cmd, flush=True)
+    try:
+        return subprocess.run(cmd, shell=True, timeout=timeout).returncode
+    except subprocess.TimeoutExpired:
+        print("TIMEOUT", cmd, flush=True)
+        return -1
+
+
+sh(f"python bench.py --steps 1000 --warmup 10 {' '.join(extra)} > gpurun_out/bench_{tag}.json 2> gpurun_out/bench_{tag}.err", 900)
+sh(f"tail -c 7000 gpurun_out/bench_{tag}.json; tail -5 gpurun_out/bench_{tag}.err")
+small = "python bench.py --steps 30 --warmup 3 --no-cpu --no-extra " + " ".join(extra)
+sh(f"ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 120 --csv "
+   f"--log-file gpurun_out/launches_{tag}.csv {small} > gpurun_out/ncu_launch_{tag}.log 2>&1", 600)
+for k in ("row_kernel", "str_kernel"):
+    sh(f"ncu --set full --clock-control none --import-source on -k regex:{k} -s 8 -c 2 -f "
+       f"-o gpurun_out/prof_{k}_{tag} {small.replace('--steps 30', '--steps 12')} > gpurun_out/ncu_full_{k}_{tag}.log 2>&1", 900)
+sh("ls -la gpurun_out")

@@ -530,14 +530,38 @@ class StrangSplittingIterator:
         handle = C.c_void_p()
         L.check(lib.ggp_plan_create(C.byref(d), C.byref(handle)))
         self.handle = handle
-        self.u = [np.ascontiguousarray(x).copy() for x in prob.u0]                      # :48
+        self._pinned = []
+        self.u = [self._pinned_like(x) for x in prob.u0]                                # :48 (pinned staging)
+        for dst, src in zip(self.u, prob.u0):
+            np.copyto(dst, src)
         L.check(lib.ggp_set_state(self.handle, _ptr_array(self.u)))
         self._step_index = 0
+
+    def _pinned_like(self, x):
+        """Page-locked host staging buffer (async DMA at full PCIe rate); plain NumPy if that fails."""
+        nbytes = int(x.size) * x.dtype.itemsize
+        ptr = self.lib.ggp_host_alloc(nbytes)
+        if not ptr:
+            return np.empty(x.shape, dtype=x.dtype)
+        self._pinned.append(ptr)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=x.dtype).reshape(x.shape)
+
+    def upload(self, u0=None):
+        """Host -> device copy of the state (`u = copy.(prob.u0)`, src/strang_splitting.jl:48)."""
+        if u0 is not None:
+            for dst, src in zip(self.u, u0):
+                np.copyto(dst, src)
+        L.check(self.lib.ggp_set_state(self.handle, _ptr_array(self.u)))
 
     def close(self):
         if getattr(self, "handle", None):
             self.lib.ggp_plan_destroy(self.handle)
             self.handle = None
+            self.u = None
+            for ptr in self._pinned:
+                self.lib.ggp_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:

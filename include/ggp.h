@@ -180,6 +180,10 @@ int64_t ggp_device_bytes(ggp_plan *plan);
    FFT_x), 1 = strided kernel with the dispersion multiply, 2 = strided forward-only / inverse-only
    (3-D middle axis), 3 = 1-D whole-step kernel.  ms_total / launches: arrays of 4. */
 int ggp_profile_enable(ggp_plan *plan, int on);
+/* Measurement aid: when bytes > 0, a buffer of that size is overwritten after EVERY kernel of ggp_step so
+   that each kernel starts with a cold L2 (timing rule for working sets smaller than the 126 MB L2).
+   The flushes are outside the per-kernel events of ggp_profile_read.  bytes = 0 switches it off. */
+int ggp_debug_l2_flush(ggp_plan *plan, uint64_t bytes);
 int ggp_profile_read(ggp_plan *plan, double *ms_total, int64_t *launches);
 
 #ifdef __cplusplus
