@@ -1,5 +1,5 @@
 """One gpurun call: headline bench, ncu launch list, ncu --set full of the two hot kernels.
-Usage on the GPU box (repo root):  python profile_round.py <tag> [bench args...]"""
+Usage on the GPU box (repo root):  python ncu_capture.py <tag> [bench args...]"""
 import os
 import subprocess
 import sys
