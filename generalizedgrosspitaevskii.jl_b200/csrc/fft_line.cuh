@@ -39,9 +39,20 @@ struct SyncWarp {
   static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
-// Stockham pass PASS (NS = product of the radices of the earlier passes) and all later passes.
-// DIR = -1 forward (e^{-i k x}), +1 inverse (unnormalised).  tw[j] = exp(-2 pi i j / N).
-template <typename T, int N, int DIR, typename SYNC, int NS>
+// Twiddle table layout (built on the host, ggp_api.cu): for every pass after the first, in order,
+// a block of (R-1)*NS entries  tw[off + (r-1)*NS + k] = exp(-2 pi i r k / (NS*R)),  k < NS, 1 <= r < R,
+// so that consecutive lanes (consecutive k) read consecutive addresses.
+template <typename T, int N>
+__host__ __device__ constexpr int twiddle_count(int NS = 1) {
+  constexpr int E = default_E<T>(N);
+  if (NS >= N) return 0;
+  const int R = (N / NS >= E) ? E : N / NS;
+  return (NS > 1 ? (R - 1) * NS : 0) + twiddle_count<T, N>(NS * R);
+}
+
+// Stockham pass (NS = product of the radices of the earlier passes) and all later passes.
+// DIR = -1 forward (e^{-i k x}), +1 inverse (unnormalised); TWOFF = offset of this pass' twiddles.
+template <typename T, int N, int DIR, typename SYNC, int NS, int TWOFF = 0>
 struct Passes {
   using Cfg = LineCfg<T, N>;
   static constexpr int E = Cfg::E;
@@ -53,8 +64,15 @@ struct Passes {
   static __device__ __forceinline__ void run(cpx<T> (&v)[E], const int t, cpx<T>* __restrict__ line,
                                              const cpx<T>* __restrict__ tw) {
     if constexpr (NS > 1) {
+      if constexpr (TPL % E == 0) {
+        // pad(t + m*TPL) = pad(t) + m*(TPL + TPL/E): one base, immediate offsets
+        const cpx<T>* rd = line + Cfg::pad(t);
 #pragma unroll
-      for (int m = 0; m < E; ++m) v[m] = line[Cfg::pad(t + m * TPL)];
+        for (int m = 0; m < E; ++m) v[m] = rd[m * (TPL + TPL / E)];
+      } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = line[Cfg::pad(t + m * TPL)];
+      }
       if constexpr (!LASTP) SYNC::sync();  // everybody has read before anybody overwrites
     }
 #pragma unroll
@@ -65,10 +83,10 @@ struct Passes {
       const int b = t + q * TPL;
       const int k = b & (NS - 1);
       if constexpr (NS > 1) {
-        constexpr int TS = N / (NS * R);
+        const cpx<T>* twk = tw + TWOFF + k;
 #pragma unroll
         for (int r = 1; r < R; ++r) {
-          const cpx<T> w = tw[r * k * TS];
+          const cpx<T> w = twk[(r - 1) * NS];
           a[r] = DIR < 0 ? cmul(a[r], w) : cmulc(a[r], w);
         }
       }
@@ -78,13 +96,25 @@ struct Passes {
         for (int r = 0; r < R; ++r) v[q + r * NB] = a[r];
       } else {
         const int base = (b - k) * R + k;
+        if constexpr (NS % E == 0) {
+          // pad(base + r*NS) = pad(base) + r*(NS + NS/E)
+          cpx<T>* wr = line + Cfg::pad(base);
 #pragma unroll
-        for (int r = 0; r < R; ++r) line[Cfg::pad(base + r * NS)] = a[r];
+          for (int r = 0; r < R; ++r) wr[r * (NS + NS / E)] = a[r];
+        } else if constexpr (NS == 1 && R == E) {
+          // first pass: base = b*E, pad(b*E + r) = b*(E+1) + r
+          cpx<T>* wr = line + b * (E + 1);
+#pragma unroll
+          for (int r = 0; r < R; ++r) wr[r] = a[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) line[Cfg::pad(base + r * NS)] = a[r];
+        }
       }
     }
     if constexpr (!LASTP) {
       SYNC::sync();
-      Passes<T, N, DIR, SYNC, NS * R>::run(v, t, line, tw);
+      Passes<T, N, DIR, SYNC, NS * R, TWOFF + (NS > 1 ? (R - 1) * NS : 0)>::run(v, t, line, tw);
     }
   }
 };

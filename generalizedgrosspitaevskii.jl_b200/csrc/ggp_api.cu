@@ -41,34 +41,33 @@ static int fail(int code, const std::string& msg) {
 
 // ---- size dispatch ---------------------------------------------------------------------------
 template <typename T>
-static int dispatch_row(int N, int M, bool pre, bool post, const RowParams<T>& p, cudaStream_t st) {
+static int dispatch_row(int N, int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
   switch (N) {
 #define X(n) \
   case n:    \
-    return launch_row<T, n>(M, pre, post, p, st);
+    return launch_row<T, n>(M, pwv, p, st);
     GGP_SIZES(X)
 #undef X
   }
   return (int)cudaErrorNotSupported;
 }
 template <typename T>
-static int dispatch_str(int N, int M, int mode, const StrParams<T>& p, long long nfast, long long nother,
-                        cudaStream_t st) {
+static int dispatch_str(int N, int M, const StrParams<T>& p, long long nfast, long long nother, cudaStream_t st) {
   switch (N) {
 #define X(n) \
   case n:    \
-    return launch_str<T, n>(M, mode, p, nfast, nother, st);
+    return launch_str<T, n>(M, p, nfast, nother, st);
     GGP_SIZES(X)
 #undef X
   }
   return (int)cudaErrorNotSupported;
 }
 template <typename T>
-static int dispatch_oned(int N, int M, const OneDParams<T>& p, cudaStream_t st) {
+static int dispatch_oned(int N, int M, int pwv, const OneDParams<T>& p, cudaStream_t st) {
   switch (N) {
 #define X(n) \
   case n:    \
-    return launch_oned<T, n>(M, p, st);
+    return launch_oned<T, n>(M, pwv, p, st);
     GGP_SIZES(X)
 #undef X
   }
@@ -301,13 +300,26 @@ struct PlanT : PlanBase {
         for (int b = 0; b < a; ++b)
           if (n[b] == n[a]) tw[a] = tw[b];
         if (tw[a]) continue;
-        std::vector<cpx<T>> h((size_t)n[a]);
-        for (long long j = 0; j < n[a]; ++j) {
-          const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n[a];
-          h[(size_t)j] = mk<T>((T)cosl(ang), (T)sinl(ang));
+        // per-pass coalesced layout, see fft_line.cuh
+        std::vector<cpx<T>> h;
+        {
+          const long long N = n[a];
+          const long long E = default_E<T>((int)N);
+          const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+          for (long long NS = 1; NS < N;) {
+            const long long R = (N / NS >= E) ? E : N / NS;
+            if (NS > 1)
+              for (long long r = 1; r < R; ++r)
+                for (long long k = 0; k < NS; ++k) {
+                  const long double ang = -twopi * (long double)(r * k) / (long double)(NS * R);
+                  h.push_back(mk<T>((T)cosl(ang), (T)sinl(ang)));
+                }
+            NS *= R;
+          }
+          if (h.empty()) h.push_back(mk<T>((T)1, (T)0));
         }
-        if ((rc = dalloc((void**)&tw[a], sizeof(cpx<T>) * (size_t)n[a]))) return rc;
-        GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(cpx<T>) * (size_t)n[a], cudaMemcpyHostToDevice));
+        if ((rc = dalloc((void**)&tw[a], sizeof(cpx<T>) * h.size()))) return rc;
+        GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(cpx<T>) * h.size(), cudaMemcpyHostToDevice));
       }
     }
     memset(&pw, 0, sizeof(pw));
@@ -411,11 +423,12 @@ struct PlanT : PlanBase {
     p.nlines = (nspatial / n[0]) * nbatch;
     p.lines_per_image = nspatial / n[0];
     p.pw = pw;
-    p.hA = hA;
-    p.hB = hB;
+    p.hs[0] = hA;
+    p.hs[1] = hB;
+    p.flags = (pre ? 1 : 0) | (post ? 2 : 0);
     int rc = prof_begin(KC_ROW);
     if (rc) return rc;
-    GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pre, post, p, stream), "row_kernel");
+    GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pw_variant(), p, stream), "row_kernel");
     ++launches;
     return prof_end();
   }
@@ -429,6 +442,7 @@ struct PlanT : PlanBase {
     p.tw = tw[ax];
     for (int i = 0; i < 4; ++i) p.D[i] = D[i];
     p.dkind = dkind;
+    p.mode = mode;
     long long nother;
     if (ax == 1) {
       p.ls = n[0];
@@ -447,9 +461,16 @@ struct PlanT : PlanBase {
     }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
-    GGP_LAUNCH(dispatch_str<T>((int)n[ax], M, mode, p, n[0], nother, stream), "str_kernel");
+    GGP_LAUNCH(dispatch_str<T>((int)n[ax], M, p, n[0], nother, stream), "str_kernel");
     ++launches;
     return prof_end();
+  }
+
+  // which compile-time variant of the half-step covers this problem (pointwise.cuh)
+  int pw_variant() const {
+    if (pw.noise) return PW_STOCH;
+    if (pw.vkind || pw.pump || pw.nl != 1) return PW_DET;
+    return PW_KERR;
   }
 
   int ensure_hs(size_t count) {
@@ -500,7 +521,7 @@ struct PlanT : PlanBase {
         for (int i = 0; i < 4; ++i) p.D[i] = D[i];
         p.dkind = dkind;
         if ((rc = prof_begin(KC_ONED))) return rc;
-        GGP_LAUNCH(dispatch_oned<T>((int)n[0], M, p, stream), "oned_kernel");
+        GGP_LAUNCH(dispatch_oned<T>((int)n[0], M, pw_variant(), p, stream), "oned_kernel");
         ++launches;
         if ((rc = prof_end())) return rc;
       }

@@ -13,35 +13,34 @@ static int set_smem(KernelT k, size_t bytes) {
   return 0;
 }
 
-template <typename T, int N, int M>
-static int launch_row_m(bool pre, bool post, const RowParams<T>& p, cudaStream_t st) {
+template <typename T, int N, int M, int PWV>
+static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   using K = KCfg<T, N>;
   const size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
   const unsigned grid = (unsigned)((p.nlines + K::LPC - 1) / K::LPC);
-  int e = 0;
-#define GGP_ROW(PRE, POST)                                                        \
-  {                                                                               \
-    auto k = row_kernel<T, N, M, PRE, POST>;                                      \
-    if ((e = set_smem(k, smem))) return e;                                        \
-    k<<<grid, K::ROW_THREADS, smem, st>>>(p);                                     \
-  }
-  if (pre && post) GGP_ROW(true, true)
-  else if (pre) GGP_ROW(true, false)
-  else if (post) GGP_ROW(false, true)
-  else GGP_ROW(false, false)
-#undef GGP_ROW
+  auto k = row_kernel<T, N, M, PWV>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  k<<<grid, K::ROW_THREADS, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int M>
+static int launch_row_m(int pwv, const RowParams<T>& p, cudaStream_t st) {
+  if (pwv == PW_KERR) return launch_row_mp<T, N, M, PW_KERR>(p, st);
+  if (pwv == PW_DET) return launch_row_mp<T, N, M, PW_DET>(p, st);
+  return launch_row_mp<T, N, M, PW_STOCH>(p, st);
+}
+
 template <typename T, int N>
-int launch_row(int M, bool pre, bool post, const RowParams<T>& p, cudaStream_t st) {
-  if (M == 1) return launch_row_m<T, N, 1>(pre, post, p, st);
-  if (M == 2) return launch_row_m<T, N, 2>(pre, post, p, st);
+int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
+  if (M == 1) return launch_row_m<T, N, 1>(pwv, p, st);
+  if (M == 2) return launch_row_m<T, N, 2>(pwv, p, st);
   return (int)cudaErrorInvalidValue;
 }
 
 template <typename T, int N, int M>
-static int launch_str_m(int mode, StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
+static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W = K::WDEF;
   while (W > nfast) W >>= 1;
@@ -52,48 +51,48 @@ static int launch_str_m(int mode, StrParams<T> p, long long nfast, long long not
   const size_t smem = K::USES_SMEM ? (size_t)W * M * p.LS * sizeof(cpx<T>) : 0;
   const long long grid = p.ntx * nother;
   if (grid > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
-  int e = 0;
-#define GGP_STR(MODE)                                                             \
-  {                                                                               \
-    auto k = str_kernel<T, N, M, MODE>;                                           \
-    if ((e = set_smem(k, smem))) return e;                                        \
-    k<<<(unsigned)grid, W * K::TPL, smem, st>>>(p);                               \
-  }
-  if (mode == 0) GGP_STR(0)
-  else if (mode == 1) GGP_STR(1)
-  else GGP_STR(2)
-#undef GGP_STR
+  auto k = str_kernel<T, N, M>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  k<<<(unsigned)grid, W * K::TPL, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
 template <typename T, int N>
-int launch_str(int M, int mode, StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
-  if (M == 1) return launch_str_m<T, N, 1>(mode, p, nfast, nother, st);
-  if (M == 2) return launch_str_m<T, N, 2>(mode, p, nfast, nother, st);
+int launch_str(int M, StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
+  if (M == 1) return launch_str_m<T, N, 1>(p, nfast, nother, st);
+  if (M == 2) return launch_str_m<T, N, 2>(p, nfast, nother, st);
   return (int)cudaErrorInvalidValue;
 }
 
-template <typename T, int N, int M>
-static int launch_oned_m(const OneDParams<T>& p, cudaStream_t st) {
+template <typename T, int N, int M, int PWV>
+static int launch_oned_mp(const OneDParams<T>& p, cudaStream_t st) {
   using K = KCfg<T, N>;
   const size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
   const unsigned grid = (unsigned)((p.nlines + K::LPC - 1) / K::LPC);
-  auto k = oned_kernel<T, N, M>;
+  auto k = oned_kernel<T, N, M, PWV>;
   int e = set_smem(k, smem);
   if (e) return e;
   k<<<grid, K::ROW_THREADS, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int M>
+static int launch_oned_m(int pwv, const OneDParams<T>& p, cudaStream_t st) {
+  if (pwv == PW_KERR) return launch_oned_mp<T, N, M, PW_KERR>(p, st);
+  if (pwv == PW_DET) return launch_oned_mp<T, N, M, PW_DET>(p, st);
+  return launch_oned_mp<T, N, M, PW_STOCH>(p, st);
+}
+
 template <typename T, int N>
-int launch_oned(int M, const OneDParams<T>& p, cudaStream_t st) {
-  if (M == 1) return launch_oned_m<T, N, 1>(p, st);
-  if (M == 2) return launch_oned_m<T, N, 2>(p, st);
+int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st) {
+  if (M == 1) return launch_oned_m<T, N, 1>(pwv, p, st);
+  if (M == 2) return launch_oned_m<T, N, 2>(pwv, p, st);
   return (int)cudaErrorInvalidValue;
 }
 
-template int launch_row<GGP_T, GGP_N>(int, bool, bool, const RowParams<GGP_T>&, cudaStream_t);
-template int launch_str<GGP_T, GGP_N>(int, int, StrParams<GGP_T>, long long, long long, cudaStream_t);
-template int launch_oned<GGP_T, GGP_N>(int, const OneDParams<GGP_T>&, cudaStream_t);
+template int launch_row<GGP_T, GGP_N>(int, int, const RowParams<GGP_T>&, cudaStream_t);
+template int launch_str<GGP_T, GGP_N>(int, StrParams<GGP_T>, long long, long long, cudaStream_t);
+template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaStream_t);
 
 }  // namespace ggp

@@ -23,7 +23,8 @@ struct RowParams {
   long long nlines;           // (nspatial / N) * nbatch
   long long lines_per_image;  // nspatial / N ; spatial table line = line % lines_per_image
   PointwiseParams<T> pw;
-  HalfStep<T> hA, hB;
+  HalfStep<T> hs[2];  // trailing half-step of step n, leading half-step of step n+1
+  int flags;          // bit 0: inverse FFT_x first, bit 1: forward FFT_x last
 };
 
 template <typename T>
@@ -36,6 +37,7 @@ struct StrParams {
   long long ts1;     // table stride of remaining dim 1 (tables do not have the batch dim)
   const cpx<T>* D[4];
   int dkind;
+  int mode;  // 0 forward only, 1 forward -> x D -> inverse, 2 inverse only
   int W, logW, LS;
 };
 
@@ -79,7 +81,49 @@ struct KCfg {
   using RowSync = typename std::conditional<(TPL <= 32), SyncWarp, SyncBlock>::type;
 };
 
-template <typename T, int N, int M, bool PRE, bool POST>
+template <typename T, int E>
+__device__ __forceinline__ void conj_all(cpx<T> (&v)[E]) {
+#pragma unroll
+  for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
+}
+
+// The forward transform is the only FFT code in a kernel; the inverse runs the same instructions
+// on conjugated data (ifft(x) = conj(fft(conj(x)))), selected by a loop that is NOT unrolled.
+// This halves the instruction footprint -- the first version of these kernels was bound by
+// instruction-cache misses (ncu: stall_no_instructions dominant, profiles/r01_notes.md).
+template <typename T, int N, int M, typename SYNC>
+__device__ __forceinline__ void fft_fwd_all(cpx<T> (&v)[M][LineCfg<T, N>::E], const int t, cpx<T>* sl, const int LS,
+                                            const cpx<T>* __restrict__ tw, const bool inverse) {
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
+    fft_line<T, N, -1, SYNC, true>(v[c], t, sl + c * LS, tw);
+    if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
+  }
+}
+
+template <typename T, int N, int M, int PWV>
+__device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], const PointwiseParams<T>& pw,
+                                           const HalfStep<T>* hs, const int nh, const long long sidx0,
+                                           const long long gidx0, const long long stride) {
+  constexpr int E = LineCfg<T, N>::E;
+#pragma unroll 1
+  for (int h = 0; h < nh; ++h) {
+    if (!hs[h].apply) continue;
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+      cpx<T> f[M];
+#pragma unroll
+      for (int c = 0; c < M; ++c) f[c] = v[c][m];
+      half_step_point<T, M, PWV>(f, pw, hs[h], sidx0 + m * stride, gidx0 + m * stride);
+#pragma unroll
+      for (int c = 0; c < M; ++c) v[c][m] = f[c];
+    }
+  }
+}
+
+// flags: bit 0 = PRE (inverse FFT_x before the half-steps), bit 1 = POST (forward FFT_x after)
+template <typename T, int N, int M, int PWV>
 __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL, LPC = K::LPC, LS = K::row_ls();
@@ -100,35 +144,10 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowP
 #pragma unroll
     for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
 
-  if (PRE) {
-#pragma unroll
-    for (int c = 0; c < M; ++c) fft_line<T, N, +1, SYNC, false>(v[c], t, sl + c * LS, p.tw);
-  }
-  if (p.hA.apply && active) {
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-      cpx<T> f[M];
-#pragma unroll
-      for (int c = 0; c < M; ++c) f[c] = v[c][m];
-      half_step_point<T, M>(f, p.pw, p.hA, soff + m * TPL, goff + m * TPL);
-#pragma unroll
-      for (int c = 0; c < M; ++c) v[c][m] = f[c];
-    }
-  }
-  if (p.hB.apply && active) {
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-      cpx<T> f[M];
-#pragma unroll
-      for (int c = 0; c < M; ++c) f[c] = v[c][m];
-      half_step_point<T, M>(f, p.pw, p.hB, soff + m * TPL, goff + m * TPL);
-#pragma unroll
-      for (int c = 0; c < M; ++c) v[c][m] = f[c];
-    }
-  }
-  if (POST) {
-#pragma unroll
-    for (int c = 0; c < M; ++c) fft_line<T, N, -1, SYNC, PRE>(v[c], t, sl + c * LS, p.tw);
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {
+    if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 0);
+    if (it == 0 && active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 2, soff, goff, TPL);
   }
   if (active) {
 #pragma unroll
@@ -138,9 +157,10 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowP
   }
 }
 
-// MODE 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
-template <typename T, int N, int M, int MODE>
-__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS) str_kernel(const StrParams<T> p) {
+// mode 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>::STR_THREADS <= 512) ? 1024 / KCfg<T, N>::STR_THREADS : 1)
+    str_kernel(const StrParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,24 +181,21 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS) str_kernel(const StrP
 #pragma unroll
     for (int m = 0; m < E; ++m) v[c][m] = p.u[c][off + m * mstride];
 
-  if (MODE != 2) {
+  const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
+#pragma unroll 1
+  for (int it = it0; it <= it1; ++it) {
+    fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
+    if (it == 0 && p.mode == 1) {
 #pragma unroll
-    for (int c = 0; c < M; ++c) fft_line<T, N, -1, SyncBlock, false>(v[c], t, sl + c * p.LS, p.tw);
-  }
-  if (MODE == 1) {
+      for (int m = 0; m < E; ++m) {
+        cpx<T> f[M];
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-      cpx<T> f[M];
+        for (int c = 0; c < M; ++c) f[c] = v[c][m];
+        disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
 #pragma unroll
-      for (int c = 0; c < M; ++c) f[c] = v[c][m];
-      disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
-#pragma unroll
-      for (int c = 0; c < M; ++c) v[c][m] = f[c];
+        for (int c = 0; c < M; ++c) v[c][m] = f[c];
+      }
     }
-  }
-  if (MODE != 0) {
-#pragma unroll
-    for (int c = 0; c < M; ++c) fft_line<T, N, +1, SyncBlock, MODE == 1>(v[c], t, sl + c * p.LS, p.tw);
   }
 #pragma unroll
   for (int c = 0; c < M; ++c)
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS) str_kernel(const StrP
     for (int m = 0; m < E; ++m) p.u[c][off + m * mstride] = v[c][m];
 }
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, int PWV>
 __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const OneDParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL, LPC = K::LPC, LS = K::row_ls();
@@ -206,35 +223,24 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const One
 #pragma unroll
     for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
 
-  for (int s = 0; s < p.nsteps; ++s) {
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const HalfStep<T> h = p.hs[2 * s + half];
-      if (h.apply && active) {
+  for (int hh = 0; hh < 2 * p.nsteps; ++hh) {
+    if (active) half_steps<T, N, M, PWV>(v, p.pw, p.hs + hh, 1, t, goff, TPL);
+    if ((hh & 1) == 0 && p.dkind != KIND_NONE) {
+#pragma unroll 1
+      for (int it = 0; it < 2; ++it) {
+        fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 1);
+        if (it == 0) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-          cpx<T> f[M];
+          for (int m = 0; m < E; ++m) {
+            cpx<T> f[M];
 #pragma unroll
-          for (int c = 0; c < M; ++c) f[c] = v[c][m];
-          half_step_point<T, M>(f, p.pw, h, t + m * TPL, goff + m * TPL);
+            for (int c = 0; c < M; ++c) f[c] = v[c][m];
+            disp_point<T, M>(f, p.D, p.dkind, t + m * TPL);
 #pragma unroll
-          for (int c = 0; c < M; ++c) v[c][m] = f[c];
+            for (int c = 0; c < M; ++c) v[c][m] = f[c];
+          }
         }
-      }
-      if (half == 0 && p.dkind != KIND_NONE) {
-#pragma unroll
-        for (int c = 0; c < M; ++c) fft_line<T, N, -1, SYNC, true>(v[c], t, sl + c * LS, p.tw);
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-          cpx<T> f[M];
-#pragma unroll
-          for (int c = 0; c < M; ++c) f[c] = v[c][m];
-          disp_point<T, M>(f, p.D, p.dkind, t + m * TPL);
-#pragma unroll
-          for (int c = 0; c < M; ++c) v[c][m] = f[c];
-        }
-#pragma unroll
-        for (int c = 0; c < M; ++c) fft_line<T, N, +1, SYNC, true>(v[c], t, sl + c * LS, p.tw);
       }
     }
   }
@@ -248,10 +254,10 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const One
 
 // ---- launchers (explicitly instantiated per (T, N) in inst.cu) --------------------------------
 template <typename T, int N>
-int launch_row(int M, bool pre, bool post, const RowParams<T>& p, cudaStream_t st);
+int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st);
 template <typename T, int N>
-int launch_str(int M, int mode, StrParams<T> p, long long nfast, long long ngroups_other, cudaStream_t st);
+int launch_str(int M, StrParams<T> p, long long nfast, long long ngroups_other, cudaStream_t st);
 template <typename T, int N>
-int launch_oned(int M, const OneDParams<T>& p, cudaStream_t st);
+int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
 
 }  // namespace ggp

@@ -40,8 +40,41 @@ struct PointwiseParams {
   long long elem_offset;  // global element index of this plan's element 0 (batch_offset * nspatial)
 };
 
-__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
-__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+// sin/cos of the nonlinear phase -dt*G.  The phase of one half-step is small in every physical run
+// (|dt*G| << 1), so the fast path is the minimax polynomial pair on [-pi/4, pi/4] (Cephes sinf/cosf,
+// sin/cos coefficients: <= 1 ulp-level error, no range reduction, ~12 FMAs); anything larger takes
+// the library routine (warp-divergent, rare).
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) {
+  if (fabsf(a) <= 0.78539816f) {
+    const float z = a * a;
+    *s = fmaf(a * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), a);
+    *c = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+              fmaf(z, -0.5f, 1.0f));
+  } else {
+    sincosf(a, s, c);
+  }
+}
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) {
+  if (fabs(a) <= 0.78539816339744830962) {
+    const double z = a * a;
+    double ps = 1.58962301576546568060e-10;
+    ps = fma(ps, z, -2.50507477628578072866e-8);
+    ps = fma(ps, z, 2.75573136213857245213e-6);
+    ps = fma(ps, z, -1.98412698295895385996e-4);
+    ps = fma(ps, z, 8.33333333332211858878e-3);
+    ps = fma(ps, z, -1.66666666666666307295e-1);
+    *s = fma(a * z, ps, a);
+    double pc = -1.13585365213876817300e-11;
+    pc = fma(pc, z, 2.08757008419747316778e-9);
+    pc = fma(pc, z, -2.75573141792967388112e-7);
+    pc = fma(pc, z, 2.48015872888517045348e-5);
+    pc = fma(pc, z, -1.38888888888730564116e-3);
+    pc = fma(pc, z, 4.16666666666665929218e-2);
+    *c = fma(z * z, pc, fma(z, -0.5, 1.0));
+  } else {
+    sincos(a, s, c);
+  }
+}
 __device__ __forceinline__ float exp_t(float a) { return expf(a); }
 __device__ __forceinline__ double exp_t(double a) { return exp(a); }
 
@@ -77,11 +110,34 @@ __device__ __forceinline__ cpx<T> philox_normal(long long gidx, uint32_t ctr, in
   return mk<T>((T)(rad * c), (T)(rad * s));
 }
 
+// Compile-time variants of the half-step (each kernel is instantiated for the three of them, so the
+// 16-fold unrolled per-point code only contains what the problem needs -- instruction-cache
+// footprint, see profiles/r01_notes.md):
+//   PW_KERR   real diagonal nonlinearity only (C1, C2, C5: scalar Kerr GPE)
+//   PW_DET    + complex nonlinearity, potential table (any kind), separable pump   (C3, bistability)
+//   PW_STOCH  + position noise (host-fed or Philox)                                (C4, windowed FT)
+enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2 };
+
 // One real-space half-step at one grid point.  sidx: index into the spatial tables; gidx: local
 // element index (spatial + batch) for noise.
-template <typename T, int M>
+template <typename T, int M, int PWV>
 __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseParams<T>& p, const HalfStep<T>& h,
                                                 const long long sidx, const long long gidx) {
+  if constexpr (PWV == PW_KERR) {
+    T n2[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) n2[j] = cabs2(f[j]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      T gre = p.nl_c_re[i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) gre += p.nl_g_re[i][j] * n2[j];
+      T s, c;
+      sincos_t(-p.dt * gre, &s, &c);
+      f[i] = cmul(mk<T>(c, s), f[i]);
+    }
+    return;
+  }
   // nonlinear phase on the pre-update field
   cpx<T> ph[M];
   if (p.nl) {
@@ -140,7 +196,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
 #pragma unroll
     for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, sv[i]);
   }
-  if (p.noise) {
+  if (PWV == PW_STOCH && p.noise) {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       cpx<T> xi;

@@ -1,0 +1,159 @@
+// Persistent, TMA-fed version of the strided-axis kernel (forward FFT -> x exp_D -> inverse FFT).
+//
+// One CTA per tile of W adjacent fast-axis positions x the whole line (N points along the strided
+// axis).  The grid is sized to the machine (resident CTAs x SMs) and every CTA walks tiles
+// tile = blockIdx.x + i*gridDim.x.  While tile i is being transformed out of registers, the TMA
+// engine (cp.async.bulk.tensor, box = [W complex] x [256 rows]) already fills the staging buffer
+// with tile i+1 and signals an mbarrier -- the load phase, which dominated the first version of this
+// kernel (ncu: stall_long_scoreboard, profiles/r01_notes.md), overlaps the butterflies.
+// The exp_D lines of the tile are pulled towards L2 with prefetch.global.L2 at tile start.
+#pragma once
+#include <cuda.h>
+#include "kernels.cuh"
+
+namespace ggp {
+
+template <typename T>
+struct alignas(64) StrTmaParams {
+  CUtensorMap map[2];  // one per field component: rank-4 tensor [2*n1 reals, n2, n3, batch]
+  cpx<T>* u[2];
+  const cpx<T>* tw;
+  long long ls;        // stride (elements) between consecutive points of a line
+  long long ntx;       // tiles of W along the fast axis
+  long long ntiles;
+  long long no1, s1, s2, ts1;
+  const cpx<T>* D[4];
+  int dkind;
+  int mode;
+  int ax;              // 1: lines along n2, 2: lines along n3
+  int W, logW, LS;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>::STR_THREADS <= 512) ? 1024 / KCfg<T, N>::STR_THREADS : 1)
+    str_tma_kernel(const __grid_constant__ StrTmaParams<T> p) {
+  using K = KCfg<T, N>;
+  constexpr int E = K::E, TPL = K::TPL;
+  constexpr int ROWS = N < 256 ? N : 256;  // TMA box rows (boxDim <= 256)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [ staging: M * N * W complex | exchange: W * M * LS complex | mbarrier ]
+  cpx<T>* stage = reinterpret_cast<cpx<T>*>(smem_raw);
+  cpx<T>* exch = stage + (size_t)M * N * p.W;
+  uint64_t* full = reinterpret_cast<uint64_t*>(exch + (size_t)p.W * M * p.LS);
+
+  const int W = p.W;
+  const int xw = threadIdx.x & (W - 1), t = threadIdx.x >> p.logW;
+  const long long mstride = (long long)TPL * p.ls;
+  cpx<T>* sl = exch + (size_t)xw * M * p.LS;
+  const uint32_t tile_bytes = (uint32_t)(M * N * W * sizeof(cpx<T>));
+
+  auto issue = [&](long long tile) {
+    const long long xt = tile % p.ntx, o = tile / p.ntx;
+    const int o1 = (int)(o % p.no1), o2 = (int)(o / p.no1);
+    mbar_expect_tx(full, tile_bytes);
+#pragma unroll 1
+    for (int c = 0; c < M; ++c)
+#pragma unroll 1
+      for (int r0 = 0; r0 < N; r0 += ROWS) {
+        cpx<T>* dst = stage + ((size_t)c * N + r0) * W;
+        if (p.ax == 1)
+          tma_load_4d(dst, &p.map[c], full, (int)(2 * xt * W), r0, o1, o2);
+        else
+          tma_load_4d(dst, &p.map[c], full, (int)(2 * xt * W), o1, r0, o2);
+      }
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && (long long)blockIdx.x < p.ntiles) issue(blockIdx.x);
+
+  uint32_t parity = 0;
+#pragma unroll 1
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long xt = tile % p.ntx, o = tile / p.ntx;
+    const long long o1 = o % p.no1, o2 = o / p.no1;
+    const long long off = xt * W + xw + o1 * p.s1 + o2 * p.s2 + (long long)t * p.ls;
+    const long long toff = xt * W + xw + o1 * p.ts1 + (long long)t * p.ls;
+    if (p.mode == 1 && p.dkind != KIND_NONE) {
+      const int nplanes = p.dkind == KIND_SCALAR ? 1 : (p.dkind == KIND_DIAG ? M : M * M);
+      for (int pl = 0; pl < nplanes; ++pl)
+#pragma unroll
+        for (int m = 0; m < E; ++m) prefetch_l2(p.D[pl] + toff + m * mstride);
+    }
+
+    mbar_wait(full, parity);
+    parity ^= 1;
+    cpx<T> v[M][E];
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[c][m] = stage[((size_t)c * N + t + m * TPL) * W + xw];
+    __syncthreads();  // staging consumed: the next tile may land
+    if (threadIdx.x == 0 && tile + gridDim.x < p.ntiles) issue(tile + gridDim.x);
+
+    const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
+#pragma unroll 1
+    for (int it = it0; it <= it1; ++it) {
+      fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
+      if (it == 0 && p.mode == 1) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          cpx<T> f[M];
+#pragma unroll
+          for (int c = 0; c < M; ++c) f[c] = v[c][m];
+          disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+#pragma unroll
+          for (int c = 0; c < M; ++c) v[c][m] = f[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int m = 0; m < E; ++m) p.u[c][off + m * mstride] = v[c][m];
+  }
+}
+
+// smem bytes needed by str_tma_kernel for a given W
+template <typename T, int N>
+inline size_t str_tma_smem(int M, int W, int LS) {
+  return sizeof(cpx<T>) * ((size_t)M * N * W + (size_t)W * M * LS) + 16;
+}
+
+template <typename T, int N>
+int launch_str_tma(int M, StrTmaParams<T> p, long long nfast, long long ngroups_other, int sm_count, cudaStream_t st);
+
+}  // namespace ggp

@@ -1,11 +1,11 @@
-"""One gpurun call: headline bench, ncu launch list, ncu --set full of the two hot kernels.
-Usage on the GPU box (repo root):  python ncu_capture.py <tag> [bench args...]"""
+"""One gpurun call: [headline bench], ncu launch list, ncu --set full of the hot kernels.
+Usage on the GPU box (repo root):  python ncu_capture.py <tag> [--no-bench] [bench args...]"""
 import os
 import subprocess
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-extra = sys.argv[2:]
+extra = [a for a in sys.argv[2:] if a != "--no-bench"]
 os.makedirs("gpurun_out", exist_ok=True)
 
 
@@ -18,12 +18,13 @@ def sh(cmd, timeout=None):
         return -1
 
 
-sh(f"python bench.py --steps 1000 --warmup 10 {' '.join(extra)} > gpurun_out/bench_{tag}.json 2> gpurun_out/bench_{tag}.err", 900)
-sh(f"tail -c 7000 gpurun_out/bench_{tag}.json; tail -5 gpurun_out/bench_{tag}.err")
+if "--no-bench" not in sys.argv:
+    sh(f"python bench.py --steps 1000 --warmup 10 {' '.join(extra)} > gpurun_out/bench_{tag}.json 2> gpurun_out/bench_{tag}.err", 900)
+    sh(f"tail -c 7000 gpurun_out/bench_{tag}.json; tail -5 gpurun_out/bench_{tag}.err")
 small = "python bench.py --steps 30 --warmup 3 --no-cpu --no-extra " + " ".join(extra)
 sh(f"ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 120 --csv "
    f"--log-file gpurun_out/launches_{tag}.csv {small} > gpurun_out/ncu_launch_{tag}.log 2>&1", 600)
 for k in ("row_kernel", "str_kernel"):
-    sh(f"ncu --set full --clock-control none --import-source on -k regex:{k} -s 8 -c 2 -f "
+    sh(f"ncu --set full --clock-control none --import-source on -k regex:{k} -s 8 -c 1 -f "
        f"-o gpurun_out/prof_{k}_{tag} {small.replace('--steps 30', '--steps 12')} > gpurun_out/ncu_full_{k}_{tag}.log 2>&1", 900)
 sh("ls -la gpurun_out")
