@@ -12,3 +12,4 @@ from .host import (  # noqa: F401
     resolve_fixed_timestepping, solve, solve_, step_,
 )
 from . import _lib as lib  # noqa: F401
+from . import parallel  # noqa: F401

@@ -2,6 +2,7 @@
 // Replaces init / step! / the inner loop of solve! of the reference (src/strang_splitting.jl:32-90,
 // src/fixed_time_stepping.jl:38-50).  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -9,7 +10,7 @@
 #include <vector>
 
 #include "../../include/ggp.h"
-#include "kernels.cuh"
+#include "str_tma.cuh"
 #include "sizes_gen.h"
 
 #ifdef GGP_WITH_NCCL
@@ -72,6 +73,30 @@ static int dispatch_oned(int N, int M, int pwv, const OneDParams<T>& p, cudaStre
 #undef X
   }
   return (int)cudaErrorNotSupported;
+}
+template <typename T>
+static int dispatch_str_tma(int N, int M, const StrTmaParams<T>& p, long long nfast, long long nother, int sms,
+                            cudaStream_t st) {
+  switch (N) {
+#define X(n) \
+  case n:    \
+    return launch_str_tma<T, n>(M, p, nfast, nother, sms, st);
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+template <typename T>
+static void dispatch_str_query(int N, long long nfast, int* W, int* LS, int* threads, int* us) {
+  *W = 0;
+  switch (N) {
+#define X(n)                                   \
+  case n:                                      \
+    str_query<T, n>(nfast, W, LS, threads, us); \
+    return;
+    GGP_SIZES(X)
+#undef X
+  }
 }
 static bool size_supported(long long n) {
   switch (n) {
@@ -188,6 +213,10 @@ struct PlanT : PlanBase {
   cpx<T>* S[2] = {nullptr, nullptr};
   cpx<T>* tw[3] = {nullptr, nullptr, nullptr};
   int dkind = 0;
+  // separable scalar dispersion: exp_D = Dperp[all but the last axis] * Dline[last axis]
+  bool sep = false;
+  cpx<T>* Dperp = nullptr;
+  cpx<T>* Dline = nullptr;
   PointwiseParams<T> pw;
   bool has_pointwise = false;
   int pump_kind = 0, noise_kind = 0, noise_real = 0;
@@ -199,6 +228,12 @@ struct PlanT : PlanBase {
   double* obs_dev = nullptr;
   cpx<T>* scratch[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
+  // TMA path of the strided kernel, per strided axis (1, 2)
+  bool tma_ok[3] = {false, false, false};
+  bool tma_d[3] = {false, false, false};  // exp_D staged by TMA as well
+  CUtensorMap tmap[3][2];
+  CUtensorMap dmap[3][4];
+  int sm_count = 148;
 
   ~PlanT() override {
     cudaSetDevice(device);
@@ -244,6 +279,50 @@ struct PlanT : PlanBase {
       if (rc) return rc;
       GGP_CUDA(cudaMemcpy(planes[c], tmp.data(), sizeof(cpx<T>) * (size_t)nspatial, cudaMemcpyHostToDevice));
     }
+    return 0;
+  }
+
+  // exp_D(k) = Dperp(k_1..k_{d-1}) * Dline(k_d) holds whenever the dispersion is a sum over axes.
+  // Checked numerically on the host table; if it holds the strided kernel never reads the full table.
+  int detect_separable(const ggp_desc& d) {
+    if (dkind != GGP_TABLE_SCALAR || ndim < 2 || getenv("GGP_NO_SEP")) return 0;
+    const long long nl = n[ndim - 1], np = nspatial / nl;
+    std::vector<std::complex<double>> tab((size_t)nspatial);
+    if (d.table_precision == GGP_C128) {
+      memcpy(tab.data(), d.disp_table, sizeof(std::complex<double>) * (size_t)nspatial);
+    } else {
+      const std::complex<float>* h = (const std::complex<float>*)d.disp_table;
+      for (long long i = 0; i < nspatial; ++i) tab[(size_t)i] = std::complex<double>(h[i].real(), h[i].imag());
+    }
+    const std::complex<double> d0 = tab[0];
+    if (std::abs(d0) == 0 || !std::isfinite(std::abs(d0))) return 0;
+    double dmax = 0, emax = 0;
+    std::vector<std::complex<double>> line((size_t)nl), perp((size_t)np);
+    for (long long l = 0; l < nl; ++l) line[(size_t)l] = tab[(size_t)(l * np)] / d0;
+    for (long long q = 0; q < np; ++q) perp[(size_t)q] = tab[(size_t)q];
+    for (long long l = 0; l < nl; ++l)
+      for (long long q = 0; q < np; ++q) {
+        const std::complex<double> z = tab[(size_t)(l * np + q)];
+        dmax = std::max(dmax, std::abs(z));
+        emax = std::max(emax, std::abs(z - perp[(size_t)q] * line[(size_t)l]));
+      }
+    // Tolerance: a table computed in the plan's precision carries a rounding error of about eps*|phase|
+    // per entry, so the factorisation cannot reproduce it better than that.  fp64: 1e-13 (keeps the
+    // accumulated deviation far below the 1e-10 parity gate); fp32: 4e-6 (~32 eps; the same size as the
+    // table's own error for phases of a few tens of radians).  GGP_NO_SEP=1 disables the fast path.
+    double tol = (d.table_precision == GGP_C128 && sizeof(T) == 8) ? 1e-13 : 4e-6;
+    if (const char* e = getenv("GGP_SEP_TOL")) tol = atof(e);
+    if (!(emax <= tol * dmax)) return 0;
+    std::vector<cpx<T>> hp((size_t)np), hl((size_t)nl);
+    const double sc = 1.0 / (double)nspatial;
+    for (long long q = 0; q < np; ++q) hp[(size_t)q] = mk<T>((T)(perp[(size_t)q].real() * sc), (T)(perp[(size_t)q].imag() * sc));
+    for (long long l = 0; l < nl; ++l) hl[(size_t)l] = mk<T>((T)line[(size_t)l].real(), (T)line[(size_t)l].imag());
+    int rc;
+    if ((rc = dalloc((void**)&Dperp, sizeof(cpx<T>) * (size_t)np))) return rc;
+    if ((rc = dalloc((void**)&Dline, sizeof(cpx<T>) * (size_t)nl))) return rc;
+    GGP_CUDA(cudaMemcpy(Dperp, hp.data(), sizeof(cpx<T>) * (size_t)np, cudaMemcpyHostToDevice));
+    GGP_CUDA(cudaMemcpy(Dline, hl.data(), sizeof(cpx<T>) * (size_t)nl, cudaMemcpyHostToDevice));
+    sep = true;
     return 0;
   }
 
@@ -294,6 +373,7 @@ struct PlanT : PlanBase {
     if (dkind != GGP_TABLE_NONE) {
       if (!d.disp_table) return fail(GGP_ERR_INVALID, "disp_table is NULL");
       if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / (double)nspatial, D))) return rc;
+      if ((rc = detect_separable(d))) return rc;
     }
     {
       for (int a = 0; a < ndim; ++a) {
@@ -367,8 +447,75 @@ struct PlanT : PlanBase {
       pw.elem_offset = batch_offset * nspatial;
     }
     has_pointwise = pw.vkind || pw.pump || pw.nl || pw.noise;
+    if ((rc = setup_tma())) return rc;
     if ((rc = dalloc((void**)&obs_dev, sizeof(double) * (size_t)(nspatial * M + 8)))) return rc;
     GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // Tensor maps for the TMA-fed strided kernel: the field as a rank-4 tensor of reals
+  // [2*n1, n2, n3, batch]; box = [2*W reals] x [min(N,256) rows along the strided axis].
+  int setup_tma() {
+    cudaDeviceProp prop;
+    GGP_CUDA(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    // The TMA-fed persistent variant is opt-in (GGP_TMA=1): with 32-byte box rows (W = 4 complex64) it
+    // measured slower than the LDG variant at two CTAs per SM on C2 (profiles/r01_notes.md).
+    if (!getenv("GGP_TMA") || getenv("GGP_NO_TMA")) return 0;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return 0;  // no TMA descriptors available: the LDG version of the kernel is used
+    }
+    EncodeFn encode = (EncodeFn)fn;
+    for (int ax = 1; ax < ndim; ++ax) {
+      int W = 0, LS = 0, threads = 0, us = 0;
+      dispatch_str_query<T>((int)n[ax], n[0], &W, &LS, &threads, &us);
+      if (!W || !us) continue;
+      const size_t esz = sizeof(cpx<T>);
+      if ((size_t)W * esz < 16 || (n[0] * esz) % 16 != 0) continue;
+      const size_t smem = esz * ((size_t)M * n[ax] * W + (size_t)W * M * LS) + 16;
+      if (smem > (size_t)prop.sharedMemPerBlockOptin) continue;
+      const cuuint32_t rows = (cuuint32_t)(n[ax] < 256 ? n[ax] : 256);
+      bool ok = true;
+      for (int c = 0; c < M && ok; ++c) {
+        cuuint64_t gdim[4] = {(cuuint64_t)(2 * n[0]), (cuuint64_t)n[1], (cuuint64_t)n[2], (cuuint64_t)nbatch};
+        cuuint64_t gstr[3] = {(cuuint64_t)(n[0] * esz), (cuuint64_t)(n[0] * n[1] * esz), (cuuint64_t)(nspatial * esz)};
+        cuuint32_t box[4] = {(cuuint32_t)(2 * W), ax == 1 ? rows : 1u, ax == 2 ? rows : 1u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmap[ax][c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                            4, (void*)u[c], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) ok = false;
+      }
+      tma_ok[ax] = ok;
+      // exp_D planes through TMA as well when the shared memory budget allows (only the axis that multiplies)
+      const int nplanes = ncols_of(dkind, M);
+      const bool last_axis = ax == ndim - 1;
+      if (ok && last_axis && nplanes > 0 && !getenv("GGP_NO_TMA_D")) {
+        const size_t smem_d = smem + esz * (size_t)nplanes * n[ax] * W;
+        if (smem_d <= (size_t)prop.sharedMemPerBlockOptin) {
+          bool okd = true;
+          for (int pl = 0; pl < nplanes && okd; ++pl) {
+            cuuint64_t gdim[4] = {(cuuint64_t)(2 * n[0]), (cuuint64_t)n[1], (cuuint64_t)n[2], 1};
+            cuuint64_t gstr[3] = {(cuuint64_t)(n[0] * esz), (cuuint64_t)(n[0] * n[1] * esz), (cuuint64_t)(nspatial * esz)};
+            cuuint32_t box[4] = {(cuuint32_t)(2 * W), ax == 1 ? rows : 1u, ax == 2 ? rows : 1u, 1u};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = encode(&dmap[ax][pl], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                4, (void*)D[pl], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) okd = false;
+          }
+          tma_d[ax] = okd;
+        }
+      }
+    }
     return 0;
   }
 
@@ -442,6 +589,11 @@ struct PlanT : PlanBase {
     p.tw = tw[ax];
     for (int i = 0; i < 4; ++i) p.D[i] = D[i];
     p.dkind = dkind;
+    if (sep && mode == 1) {
+      p.D[0] = Dperp;
+      p.D[1] = Dline;
+      p.dkind = KIND_SEP;
+    }
     p.mode = mode;
     long long nother;
     if (ax == 1) {
@@ -461,6 +613,29 @@ struct PlanT : PlanBase {
     }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
+    if (tma_ok[ax]) {
+      StrTmaParams<T> q;
+      memset(&q, 0, sizeof(q));
+      for (int c = 0; c < M; ++c) q.map[c] = tmap[ax][c];
+      q.u[0] = u[0];
+      q.u[1] = u[1];
+      q.tw = p.tw;
+      q.ls = p.ls;
+      q.no1 = p.no1;
+      q.s1 = p.s1;
+      q.s2 = p.s2;
+      q.ts1 = p.ts1;
+      for (int i = 0; i < 4; ++i) q.D[i] = p.D[i];
+      q.dkind = p.dkind;
+      q.mode = mode;
+      q.ax = ax;
+      q.nplanes = ncols_of(dkind, M);
+      q.stage_d = (mode == 1 && tma_d[ax] && p.dkind != KIND_SEP) ? 1 : 0;
+      for (int i = 0; i < 4; ++i) q.dmap[i] = dmap[ax][i];
+      GGP_LAUNCH(dispatch_str_tma<T>((int)n[ax], M, q, n[0], nother, sm_count, stream), "str_tma_kernel");
+      ++launches;
+      return prof_end();
+    }
     GGP_LAUNCH(dispatch_str<T>((int)n[ax], M, p, n[0], nother, stream), "str_kernel");
     ++launches;
     return prof_end();

@@ -1,6 +1,7 @@
 // One translation unit per (GGP_T, GGP_N): explicit instantiation of the launchers, so the
 // library builds in parallel.  Compiled with -DGGP_T=float|double -DGGP_N=<line length>.
-#include "kernels.cuh"
+#include <cstdlib>
+#include "str_tma.cuh"
 
 namespace ggp {
 
@@ -39,11 +40,57 @@ int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
   return (int)cudaErrorInvalidValue;
 }
 
+template <typename T, int N>
+void str_query(long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
+  using K = KCfg<T, N>;
+  int W = K::WDEF;
+  if (const char* e = getenv("GGP_STR_W")) {  // tuning knob
+    const int w = atoi(e);
+    if (w >= 1 && w <= K::WDEF && (w & (w - 1)) == 0) W = w;
+  }
+  while (W > nfast) W >>= 1;
+  *W_ = W;
+  *LS_ = K::str_ls(W);
+  *threads = W * K::TPL;
+  *uses_smem = K::USES_SMEM ? 1 : 0;
+}
+
+template <typename T, int N, int M>
+static int launch_str_tma_m(StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
+  using K = KCfg<T, N>;
+  int W, LS, threads, us;
+  str_query<T, N>(nfast, &W, &LS, &threads, &us);
+  p.W = W;
+  p.logW = ilog2(W);
+  p.LS = LS;
+  p.ntx = nfast / W;
+  p.ntiles = p.ntx * nother;
+  const size_t smem = str_tma_smem<T, N>(M, W, LS, p.stage_d ? p.nplanes : 0);
+  auto k = str_tma_kernel<T, N, M>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  int per_sm = 0;
+  cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
+  if (ce != cudaSuccess) return (int)ce;
+  if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+  long long grid = (long long)per_sm * sm_count;
+  if (grid > p.ntiles) grid = p.ntiles;
+  k<<<(unsigned)grid, threads, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int N>
+int launch_str_tma(int M, StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
+  if (M == 1) return launch_str_tma_m<T, N, 1>(p, nfast, nother, sm_count, st);
+  if (M == 2) return launch_str_tma_m<T, N, 2>(p, nfast, nother, sm_count, st);
+  return (int)cudaErrorInvalidValue;
+}
+
 template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
-  int W = K::WDEF;
-  while (W > nfast) W >>= 1;
+  int W, LS_, threads_, us_;
+  str_query<T, N>(nfast, &W, &LS_, &threads_, &us_);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = K::str_ls(W);
@@ -94,5 +141,7 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st) {
 template int launch_row<GGP_T, GGP_N>(int, int, const RowParams<GGP_T>&, cudaStream_t);
 template int launch_str<GGP_T, GGP_N>(int, StrParams<GGP_T>, long long, long long, cudaStream_t);
 template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaStream_t);
+template int launch_str_tma<GGP_T, GGP_N>(int, StrTmaParams<GGP_T>, long long, long long, int, cudaStream_t);
+template void str_query<GGP_T, GGP_N>(long long, int*, int*, int*, int*);
 
 }  // namespace ggp

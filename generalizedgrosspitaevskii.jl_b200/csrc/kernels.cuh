@@ -186,14 +186,25 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
   for (int it = it0; it <= it1; ++it) {
     fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
     if (it == 0 && p.mode == 1) {
+      if (p.dkind == KIND_SEP) {
+        const cpx<T> dperp = p.D[0][toff - (long long)t * p.ls];
+        const cpx<T>* dline = p.D[1] + t;
 #pragma unroll
-      for (int m = 0; m < E; ++m) {
-        cpx<T> f[M];
+        for (int m = 0; m < E; ++m) {
+          const cpx<T> d = cmul(dperp, dline[m * TPL]);
 #pragma unroll
-        for (int c = 0; c < M; ++c) f[c] = v[c][m];
-        disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+          for (int c = 0; c < M; ++c) v[c][m] = cmul(d, v[c][m]);
+        }
+      } else {
 #pragma unroll
-        for (int c = 0; c < M; ++c) v[c][m] = f[c];
+        for (int m = 0; m < E; ++m) {
+          cpx<T> f[M];
+#pragma unroll
+          for (int c = 0; c < M; ++c) f[c] = v[c][m];
+          disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+#pragma unroll
+          for (int c = 0; c < M; ++c) v[c][m] = f[c];
+        }
       }
     }
   }
@@ -259,5 +270,9 @@ template <typename T, int N>
 int launch_str(int M, StrParams<T> p, long long nfast, long long ngroups_other, cudaStream_t st);
 template <typename T, int N>
 int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
+// geometry of the strided kernels for a fast axis of nfast points: W (coalescing width), padded
+// line stride LS, threads per CTA, and whether the line needs the shared exchange buffer
+template <typename T, int N>
+void str_query(long long nfast, int* W, int* LS, int* threads, int* uses_smem);
 
 }  // namespace ggp

@@ -9,7 +9,10 @@
 
 namespace ggp {
 
-enum { KIND_NONE = 0, KIND_SCALAR = 1, KIND_DIAG = 2, KIND_FULL = 3 };
+// KIND_SEP: a scalar exp_D that factorises as D_perp[other axes] * D_line[strided axis] (true whenever the
+// dispersion is a sum over axes, e.g. |k|^2/2): the strided kernel then reads one D_perp value per
+// thread and a cache-resident vector instead of a full-grid table.
+enum { KIND_NONE = 0, KIND_SCALAR = 1, KIND_DIAG = 2, KIND_FULL = 3, KIND_SEP = 4 };
 enum { NOISE_OFF = 0, NOISE_HOST = 1, NOISE_PHILOX = 2 };
 
 // per-half-step scalars

@@ -15,7 +15,10 @@ namespace ggp {
 
 template <typename T>
 struct alignas(64) StrTmaParams {
-  CUtensorMap map[2];  // one per field component: rank-4 tensor [2*n1 reals, n2, n3, batch]
+  CUtensorMap map[2];   // one per field component: rank-4 tensor [2*n1 reals, n2, n3, batch]
+  CUtensorMap dmap[4];  // exp_D planes as [2*n1, n2, n3, 1] (used when stage_d)
+  int stage_d;          // 1: the exp_D tile is staged through shared memory by TMA as well
+  int nplanes;          // planes of exp_D (1, M or M*M)
   cpx<T>* u[2];
   const cpx<T>* tw;
   long long ls;        // stride (elements) between consecutive points of a line
@@ -65,11 +68,13 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
   constexpr int ROWS = N < 256 ? N : 256;  // TMA box rows (boxDim <= 256)
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [ staging: M * N * W complex | exchange: W * M * LS complex | mbarrier ]
-  cpx<T>* stage = reinterpret_cast<cpx<T>*>(smem_raw);
-  cpx<T>* exch = stage + (size_t)M * N * p.W;
+  extern __shared__ __align__(128) unsigned char smem_tma_raw[];
+  // [ staging: M * N * W complex | exp_D staging: nplanes * N * W (optional) | exchange: W * M * LS | mbarriers ]
+  cpx<T>* stage = reinterpret_cast<cpx<T>*>(smem_tma_raw);
+  cpx<T>* stage_d = stage + (size_t)M * N * p.W;
+  cpx<T>* exch = stage_d + (p.stage_d ? (size_t)p.nplanes * N * p.W : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(exch + (size_t)p.W * M * p.LS);
+  uint64_t* full_d = full + 1;
 
   const int W = p.W;
   const int xw = threadIdx.x & (W - 1), t = threadIdx.x >> p.logW;
@@ -93,12 +98,34 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
       }
   };
 
+  const bool use_d = p.mode == 1 && p.dkind != KIND_NONE;
+  const bool staged_d = use_d && p.stage_d && p.dkind != KIND_SEP;
+  auto issue_d = [&](long long tile) {
+    const long long xt = tile % p.ntx, o = tile / p.ntx;
+    const int o1 = (int)(o % p.no1);
+    mbar_expect_tx(full_d, (uint32_t)(p.nplanes * N * W * sizeof(cpx<T>)));
+#pragma unroll 1
+    for (int pl = 0; pl < p.nplanes; ++pl)
+#pragma unroll 1
+      for (int r0 = 0; r0 < N; r0 += ROWS) {
+        cpx<T>* dst = stage_d + ((size_t)pl * N + r0) * W;
+        if (p.ax == 1)
+          tma_load_4d(dst, &p.dmap[pl], full_d, (int)(2 * xt * W), r0, o1, 0);
+        else
+          tma_load_4d(dst, &p.dmap[pl], full_d, (int)(2 * xt * W), o1, r0, 0);
+      }
+  };
+
   if (threadIdx.x == 0) {
     mbar_init(full, 1);
+    mbar_init(full_d, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0 && (long long)blockIdx.x < p.ntiles) issue(blockIdx.x);
+  if (threadIdx.x == 0 && (long long)blockIdx.x < p.ntiles) {
+    issue(blockIdx.x);
+    if (staged_d) issue_d(blockIdx.x);
+  }
 
   uint32_t parity = 0;
 #pragma unroll 1
@@ -107,9 +134,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
     const long long o1 = o % p.no1, o2 = o / p.no1;
     const long long off = xt * W + xw + o1 * p.s1 + o2 * p.s2 + (long long)t * p.ls;
     const long long toff = xt * W + xw + o1 * p.ts1 + (long long)t * p.ls;
-    if (p.mode == 1 && p.dkind != KIND_NONE) {
-      const int nplanes = p.dkind == KIND_SCALAR ? 1 : (p.dkind == KIND_DIAG ? M : M * M);
-      for (int pl = 0; pl < nplanes; ++pl)
+    if (use_d && !staged_d && p.dkind != KIND_SEP) {
+      for (int pl = 0; pl < p.nplanes; ++pl)
 #pragma unroll
         for (int m = 0; m < E; ++m) prefetch_l2(p.D[pl] + toff + m * mstride);
     }
@@ -129,14 +155,42 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
     for (int it = it0; it <= it1; ++it) {
       fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
       if (it == 0 && p.mode == 1) {
+        if (staged_d) {
+          // exp_D of this tile sits in shared memory [plane][row][W]
+          mbar_wait(full_d, parity ^ 1);
+          const cpx<T>* dpl[4];
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-          cpx<T> f[M];
+          for (int i = 0; i < 4; ++i) dpl[i] = stage_d + (size_t)i * N * W;
 #pragma unroll
-          for (int c = 0; c < M; ++c) f[c] = v[c][m];
-          disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+          for (int m = 0; m < E; ++m) {
+            cpx<T> f[M];
 #pragma unroll
-          for (int c = 0; c < M; ++c) v[c][m] = f[c];
+            for (int c = 0; c < M; ++c) f[c] = v[c][m];
+            disp_point<T, M>(f, dpl, p.dkind, (long long)(t + m * TPL) * W + xw);
+#pragma unroll
+            for (int c = 0; c < M; ++c) v[c][m] = f[c];
+          }
+          __syncthreads();  // exp_D staging consumed
+          if (threadIdx.x == 0 && tile + gridDim.x < p.ntiles) issue_d(tile + gridDim.x);
+        } else if (p.dkind == KIND_SEP) {
+          const cpx<T> dperp = p.D[0][toff - (long long)t * p.ls];
+          const cpx<T>* dline = p.D[1] + t;
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const cpx<T> d = cmul(dperp, dline[m * TPL]);
+#pragma unroll
+            for (int c = 0; c < M; ++c) v[c][m] = cmul(d, v[c][m]);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            cpx<T> f[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) f[c] = v[c][m];
+            disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+#pragma unroll
+            for (int c = 0; c < M; ++c) v[c][m] = f[c];
+          }
         }
       }
     }
@@ -149,8 +203,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
 
 // smem bytes needed by str_tma_kernel for a given W
 template <typename T, int N>
-inline size_t str_tma_smem(int M, int W, int LS) {
-  return sizeof(cpx<T>) * ((size_t)M * N * W + (size_t)W * M * LS) + 16;
+inline size_t str_tma_smem(int M, int W, int LS, int dplanes) {
+  return sizeof(cpx<T>) * ((size_t)M * N * W + (size_t)dplanes * N * W + (size_t)W * M * LS) + 16;
 }
 
 template <typename T, int N>

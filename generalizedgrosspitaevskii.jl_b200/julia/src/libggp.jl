@@ -1,0 +1,102 @@
+# Thin ccall layer over libggp.so (include/ggp.h).  Nothing here computes: every grid-sized
+# floating-point operation of the time loop happens inside the CUDA library.
+#
+# NOTE: written without a Julia toolchain in the build image (SURVEY: "No Julia anywhere in the
+# loop"); kept deliberately small and mechanical so that it can be reviewed by eye.  The Python host
+# mirror (../host.py) implements the same logic line for line and IS exercised by the test-suite.
+using Libdl
+
+const GGP_ABI_VERSION = UInt32(1)
+const GGP_C64, GGP_C128 = Int32(0), Int32(1)
+const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL = Int32(0), Int32(1), Int32(2), Int32(3)
+
+# Mirror of `struct ggp_desc`; field order and types must match include/ggp.h exactly
+# (tests/test_host_logic.py checks the ctypes twin of this struct against the C header).
+struct GgpDesc
+    abi_version::UInt32
+    struct_size::UInt32
+    ndim::Int32
+    ncomp::Int32
+    n::NTuple{3,Int64}
+    nbatch::Int64
+    batch_offset::Int64
+    precision::Int32
+    table_precision::Int32
+    device::Int32
+    reserved0::Int32
+    stream::Ptr{Cvoid}
+    dt::Float64
+    disp_kind::Int32
+    pot_kind::Int32
+    disp_table::Ptr{Cvoid}
+    pot_table::Ptr{Cvoid}
+    nl_kind::Int32
+    nl_scalar::Int32
+    nl_c::NTuple{4,Float64}      # [i][re/im]
+    nl_g::NTuple{8,Float64}      # [i][j][re/im]
+    pump_kind::Int32
+    pump_ncomp::Int32
+    pump_table::Ptr{Cvoid}
+    pump_amp0::NTuple{2,Float64}
+    noise_kind::Int32
+    noise_real::Int32
+    noise_eta::NTuple{4,Float64}
+    seed::UInt64
+end
+
+const _lib = Ref{Ptr{Cvoid}}(C_NULL)
+
+function _handle()
+    if _lib[] == C_NULL
+        path = get(ENV, "GGP_LIBRARY", joinpath(@__DIR__, "..", "..", "libggp.so"))
+        _lib[] = Libdl.dlopen(path)          # throws if missing: there is no CPU fallback
+    end
+    _lib[]
+end
+
+_sym(name::Symbol) = Libdl.dlsym(_handle(), name)
+
+function _check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall(_sym(:ggp_last_error), Cstring, ()))
+    error("libggp error $rc: $msg")
+end
+
+function ggp_plan_create(desc::GgpDesc)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall(_sym(:ggp_plan_create), Cint, (Ref{GgpDesc}, Ref{Ptr{Cvoid}}), desc, out))
+    out[]
+end
+
+ggp_plan_destroy(h::Ptr{Cvoid}) = (ccall(_sym(:ggp_plan_destroy), Cint, (Ptr{Cvoid},), h); nothing)
+
+function ggp_set_state(h::Ptr{Cvoid}, u::NTuple{M,<:Array}) where {M}
+    ptrs = Ptr{Cvoid}[pointer(x) for x in u]
+    GC.@preserve u ptrs _check(ccall(_sym(:ggp_set_state), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), h, ptrs))
+end
+
+# dest: tuple of contiguous views/arrays (one per component)
+function ggp_get_state(h::Ptr{Cvoid}, dest::NTuple{M,Any}) where {M}
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(x)) for x in dest]
+    GC.@preserve dest ptrs _check(ccall(_sym(:ggp_get_state), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), h, ptrs))
+end
+
+# amps: 2 x nsteps ComplexF64 (column s = [a(t_s + dt/2), a(t_s + dt)]) or nothing (static / no pump)
+function ggp_step(h::Ptr{Cvoid}, nsteps::Integer, amps::Union{Nothing,AbstractMatrix{ComplexF64}})
+    if amps === nothing
+        _check(ccall(_sym(:ggp_step), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Ptr{Cvoid}}), h, nsteps, C_NULL, C_NULL))
+    else
+        a = Matrix{ComplexF64}(amps)
+        GC.@preserve a _check(ccall(_sym(:ggp_step), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
+            h, nsteps, Ptr{Float64}(pointer(a)), C_NULL))
+    end
+end
+
+# TEST MODE: feed the reference's own noise buffers (step, half-step, component order)
+function ggp_step_with_noise(h::Ptr{Cvoid}, nsteps::Integer, amps, noise::Vector{<:Array})
+    ptrs = Ptr{Cvoid}[pointer(x) for x in noise]
+    a = amps === nothing ? nothing : Matrix{ComplexF64}(amps)
+    pa = a === nothing ? Ptr{Float64}(C_NULL) : Ptr{Float64}(pointer(a))
+    GC.@preserve noise ptrs a _check(ccall(_sym(:ggp_step), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
+        h, nsteps, pa, ptrs))
+end

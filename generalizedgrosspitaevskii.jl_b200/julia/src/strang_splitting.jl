@@ -1,0 +1,135 @@
+# Drop-in replacement for the reference's src/strang_splitting.jl + src/kernels.jl and for the inner
+# loop of src/fixed_time_stepping.jl: same `StrangSplitting`, same `init / step! / solve! / solve`
+# signatures and return types; the time loop runs in libggp.so.
+#
+# What stays Julia (SURVEY §8b): resolve_fixed_timestepping (kept verbatim in fixed_time_stepping.jl),
+# the exp tables through the reference's own get_exponential on HOST arrays (exact parity, arbitrary
+# closures), `ts` accumulation in type T, ProgressMeter, result allocation, RNG seed derivation.
+
+struct StrangSplitting <: FixedTimeSteppingAlgorithm end
+
+mutable struct StrangSplittingIterator{PROB,T,PROG1,PROG2,R,A} <: FixedTimeSteppingIterator
+    prob::PROB
+    dt::T
+    ts::Vector{T}
+    steps_per_save::Int
+    save_start::Bool
+    progress::PROG1
+    given_progress::PROG2
+    result::R
+    handle::Ptr{Cvoid}
+    amps::A                 # 2 × nsteps ComplexF64, or nothing (static pump / no pump)
+    step_index::Int
+end
+
+_kind(::MultiplicativeIdentity) = GGP_TABLE_NONE
+_kind(::Array{<:Number}) = GGP_TABLE_SCALAR
+_kind(::Array{<:SVector}) = GGP_TABLE_DIAG
+_kind(::Array{<:SMatrix}) = GGP_TABLE_FULL
+# host table -> ComplexF64 array-of-structs exactly as Julia lays it out (point-major, static entries column-major)
+_flat(::MultiplicativeIdentity) = ComplexF64[]
+_flat(t::Array{<:Number}) = ComplexF64.(vec(t))
+_flat(t::Array{<:StaticArray}) = ComplexF64[x for s in vec(t) for x in s]
+_ptr(v::Vector{ComplexF64}) = isempty(v) ? Ptr{Cvoid}(C_NULL) : Ptr{Cvoid}(pointer(v))
+
+function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
+    dt, nsaves, show_progress=true, progress=nothing, save_start=true, workgroup_size=(), rng=nothing,
+    device=-1, batch_offset=0) where {N,M}
+
+    result = map(x -> stack(x for _ ∈ 1:nsaves+save_start), prob.u0)                  # reference :41-43
+    dt, ts, steps_per_save = resolve_fixed_timestepping(dt, tspan, nsaves)            # :45
+    _progress = _Progress(progress, steps_per_save * nsaves; enabled=show_progress)    # :46
+
+    CT = eltype(first(prob.u0))
+    CT <: Union{ComplexF32,ComplexF64} || error("fields must be ComplexF32 or ComplexF64")
+    sz = size(first(prob.u0))
+    nspatial = prod(sz[1:N]); nbatch = prod(sz[N+1:end])
+
+    # tables: the reference's own get_exponential on host arrays (src/misc.jl:12-20)
+    rg, dg = reciprocal_grid(prob), direct_grid(prob)
+    host_u0 = map(Array, prob.u0)
+    exp_D = get_exponential(prob.dispersion, host_u0, rg, prob.param, dt)             # :53 (full dt)
+    exp_V = get_exponential(prob.potential, host_u0, dg, prob.param, dt / 2)          # :54
+    # 1x1 wrappers (SVector{1}, SMatrix{1,1}) collapse to scalars; M-vectors / MxM matrices keep their kind
+    dflat, vflat = _flat(exp_D), _flat(exp_V)
+    dkind = (M == 1 && _kind(exp_D) != GGP_TABLE_NONE) ? GGP_TABLE_SCALAR : _kind(exp_D)
+    vkind = (M == 1 && _kind(exp_V) != GGP_TABLE_NONE) ? GGP_TABLE_SCALAR : _kind(exp_V)
+
+    nl_kind = Int32(0); nl_scalar = Int32(0); nl_c = ntuple(_ -> 0.0, 4); nl_g = ntuple(_ -> 0.0, 8)
+    if !(prob.nonlinearity isa AdditiveIdentity)
+        sc, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, Val(M))
+        nl_kind = Int32(1); nl_scalar = Int32(sc)
+        nl_c = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(c[i]) : imag(c[i]))), 4)
+        nl_g = ntuple(k -> begin
+                i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
+                (i > M || j > M) ? 0.0 : (isodd(k) ? real(g[i, j]) : imag(g[i, j]))
+            end, 8)
+    end
+
+    # pump amplitudes at the reference's times: t is incremented BEFORE step! (SURVEY Q1)
+    nsteps = nsaves * steps_per_save
+    pump_kind = Int32(0); pump_ncomp = Int32(0); sflat = ComplexF64[]; amp0 = (0.0, 0.0); amps = nothing
+    if !(prob.pump isa AdditiveIdentity)
+        t = ts[1]; times = Vector{typeof(t)}(undef, 2nsteps)
+        for s in 1:nsteps
+            t += dt; times[2s-1] = t + dt / 2; times[2s] = t + dt
+        end
+        S, ncomp, amp = recognise_pump(prob.pump, prob, tspan, times)
+        pump_kind = Int32(1); pump_ncomp = Int32(ncomp); sflat = vec(S)               # point-major, then component
+        a0 = amp(ts[1]); amp0 = (real(a0), imag(a0))                                  # primed at tspan[1], :58
+        A = ComplexF64[amp(times[k]) for k in 1:2nsteps]
+        amps = all(==(a0), A) ? nothing : reshape(A, 2, nsteps)
+    end
+
+    noise_kind = Int32(0); noise_real = Int32(0); eta = ntuple(_ -> 0.0, 4); seed = UInt64(0)
+    if !(prob.position_noise_func isa AdditiveIdentity)
+        e = recognise_noise(prob.position_noise_func, prob)
+        noise_kind = Int32(1); noise_real = Int32(eltype(first(prob.noise_prototype)) <: Real)
+        eta = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(e[i]) : imag(e[i]))), 4)
+        seed = rng === nothing ? rand(UInt64) : rand(rng, UInt64)
+    end
+
+    desc = GgpDesc(GGP_ABI_VERSION, UInt32(sizeof(GgpDesc)), Int32(N), Int32(M),
+        ntuple(i -> i ≤ N ? Int64(sz[i]) : Int64(1), 3), Int64(nbatch), Int64(batch_offset),
+        CT == ComplexF32 ? GGP_C64 : GGP_C128, GGP_C128, Int32(device), Int32(0), C_NULL, Float64(dt),
+        dkind, vkind, _ptr(dflat), _ptr(vflat), nl_kind, nl_scalar, nl_c, nl_g,
+        pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed)
+    handle = GC.@preserve dflat vflat sflat ggp_plan_create(desc)
+    ggp_set_state(handle, host_u0)                                                    # u = copy.(prob.u0), :48
+
+    iter = StrangSplittingIterator(prob, dt, ts, steps_per_save, save_start, _progress, progress, result,
+        handle, amps, 0)
+    finalizer(it -> (it.handle == C_NULL || ggp_plan_destroy(it.handle); it.handle = C_NULL), iter)
+    iter
+end
+
+# step!(iter, t, dt): one Strang step on the device (reference :86-90).  t/dt are accepted for
+# signature compatibility; the pump schedule was fixed at init.
+function step!(iter::StrangSplittingIterator, t, dt)
+    a = iter.amps === nothing ? nothing : view(iter.amps, :, iter.step_index+1:iter.step_index+1)
+    ggp_step(iter.handle, 1, a)
+    iter.step_index += 1
+    nothing
+end
+
+# solve!: the reference's loop (src/fixed_time_stepping.jl:26-54) with the inner `for _ in 1:steps_per_save`
+# batched into one ggp_step call and `map(copy!, slice, iter.u)` replaced by one D2H per save.
+function solve!(iter::StrangSplittingIterator)
+    save_start, sps, dt, p, ts = iter.save_start, iter.steps_per_save, iter.dt, iter.progress, iter.ts
+    nd = ndims(first(iter.result))
+    t = ts[1]
+    for n ∈ 1:size(first(iter.result), nd)-save_start
+        a = iter.amps === nothing ? nothing : view(iter.amps, :, iter.step_index+1:iter.step_index+sps)
+        ggp_step(iter.handle, sps, a)
+        iter.step_index += sps
+        for _ ∈ 1:sps
+            t += dt                                   # accumulated in T exactly like the reference (:44)
+            _next!(p)
+        end
+        slices = map(x -> selectdim(x, nd, n + save_start), iter.result)   # contiguous: last dim
+        ggp_get_state(iter.handle, slices)
+        ts[n+1] = t
+    end
+    _finish!(p, iter.given_progress)
+    ts[begin+1-save_start:end], iter.result
+end

@@ -1,0 +1,73 @@
+"""Generate tests/golden/golden_v1.npz from the CPU oracle (oracle/ggp_oracle.py).
+
+The reference ships no golden vectors and cannot be executed in this image (no Julia), so these
+fixtures pin the ORACLE (itself pinned by the reference's known-answer tests,
+tests/test_oracle_known_answers.py) for regression, and give the GPU tests a committed target that
+does not depend on re-running the oracle.   Usage:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = {
+    # name: (factory, kwargs, noise_seed)
+    "kerr2d_c128": ("kerr2d", dict(N=32, dtype="complex128", nsteps=8, L=16.0), None),
+    "kerr2d_c64": ("kerr2d", dict(N=32, dtype="complex64", nsteps=8, L=16.0), None),
+    "quick_start_kerr": ("quick_start", dict(N=32, kerr=True), None),
+    "exciton_polariton": ("exciton_polariton", dict(N=16, nsaves=4, tspan=(0, 1.5625)), None),
+    "exciton_polariton_time_pump": ("exciton_polariton", dict(N=16, nsaves=2, tspan=(0, 1.6), dt=0.05, time_pump=True), None),
+    "bistability": ("bistability", dict(n=64, nsaves=4, tspan=(0, 25.78125)), None),
+    "windowed_ft_noise": ("windowed_ft", dict(ntraj=8), 11),
+    "truncated_wigner_2d_noise": ("truncated_wigner", dict(ntraj=4, N=16, ndim=2, tspan=(0, 0.5)), 5),
+    "kerr3d_c128": ("kerr3d", dict(N=8, dtype="complex128", nsteps=4, L=8.0), None),
+}
+
+
+def noise_source_for(seed):
+    rng = np.random.default_rng(seed)
+
+    def src(shape, dtype):
+        if np.issubdtype(dtype, np.complexfloating):
+            return ((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)).astype(dtype)
+        return rng.standard_normal(shape).astype(dtype)
+    return src
+
+
+def build(ns, name):
+    import problems as P
+    fac, kw, seed = CASES[name]
+    kw = dict(kw)
+    if "dtype" in kw:
+        kw["dtype"] = np.dtype(kw["dtype"]).type
+    return getattr(P, fac)(ns, **kw), seed
+
+
+def run_oracle(name, record=None):
+    import ggp_oracle as O
+    pb, seed = build(O, name)
+    prob = O.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    kw = {}
+    if seed is not None:
+        kw = dict(noise_source=noise_source_for(seed), record_noise=record)
+    ts, sol = O.solve(prob, O.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"],
+                      save_start=pb.get("save_start", True), **kw)
+    return ts, sol
+
+
+if __name__ == "__main__":
+    out = {}
+    for name in CASES:
+        ts, sol = run_oracle(name)
+        out[name + "/ts"] = ts
+        for c, s in enumerate(sol):
+            out[f"{name}/u{c}"] = s[-1]          # final save only (keeps the fixture small)
+        print(name, [s.shape for s in sol], float(np.abs(sol[0][-1]).max()))
+    path = os.path.join(HERE, "golden_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")

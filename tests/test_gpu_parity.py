@@ -75,6 +75,18 @@ def test_c2_shape_kerr2d(G, dtype):
         assert rel_l2(g, ref64) <= 1e-4
 
 
+def test_c2_c64_1000_step_prefix(G):
+    """SURVEY hard part 5: the ComplexF32 gate (<= 1e-4) on a 1000-step prefix of C2's problem (256^2),
+    against the fp32 oracle AND the fp64 oracle; the three mutual distances are printed."""
+    g, o32 = run_both(G, P.kerr2d, N=256, dtype=np.complex64, nsteps=1000)
+    pb = P.kerr2d(O, N=256, dtype=np.complex128, nsteps=1000)
+    prob = O.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    _, o64 = O.solve(prob, O.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=1)
+    d_g32, d_g64, d_3264 = rel_l2(g, o32), rel_l2(g, o64), rel_l2(o32, o64)
+    print(f"\nc64 1000 steps: ours-fp32oracle {d_g32:.3e}  ours-fp64oracle {d_g64:.3e}  fp32oracle-fp64oracle {d_3264:.3e}")
+    assert d_g32 <= 1e-4 and d_g64 <= 1e-4
+
+
 def test_bistability_prefix_and_wrappers(G):
     """test/bistability_cycle.jl on a prefix of the run (time-dependent separable pump, lossy
     dispersion, Kerr) + the 27 scalar/SVector/SMatrix{1,1} wrappings (:67-71)."""

@@ -1,0 +1,159 @@
+"""CPU-only tests of the host side of the backend (no compute calls: there is no GPU here and no
+CPU fallback): the C-ABI library loads and exports every symbol include/ggp.h declares, the ctypes
+mirror of ggp_desc matches the C layout, and the closure-recognition / table / schedule logic agrees
+with the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import ggp_oracle as O
+import problems as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import ggp_b200
+    return ggp_b200
+
+
+def test_library_loads_and_exports_header_symbols(G):
+    lib = G.load()
+    hdr = open(os.path.join(ROOT, "include", "ggp.h")).read()
+    declared = set(re.findall(r"\b(ggp_[a-z0-9_]+)\s*\(", hdr))
+    assert {"ggp_plan_create", "ggp_step", "ggp_set_state", "ggp_get_state", "ggp_plan_destroy"} <= declared
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ggp.h but not exported by libggp.so"
+    assert set(G.lib.EXPORTS) <= declared
+    assert lib.ggp_version() >= 100
+
+
+def test_desc_layout_matches_c_header(G):
+    """Compile a tiny C program against include/ggp.h and compare sizeof/offsetof with the ctypes mirror."""
+    fields = [f[0] for f in G.lib.GgpDesc._fields_]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "ggp.h"\nint main(){printf("%zu\\n", sizeof(ggp_desc));\n'
+    for f in fields:
+        src += f'printf("%zu\\n", offsetof(ggp_desc, {f}));\n'
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == C.sizeof(G.lib.GgpDesc)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(G.lib.GgpDesc, f).offset == int(off), f
+
+
+def test_no_cpu_fallback(G):
+    """Without a CUDA device plan creation fails loudly with GGP_ERR_CUDA."""
+    lib = G.load()
+    if lib.ggp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    pb = P.quick_start(G, N=16)
+    prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    with pytest.raises(G.GgpError) as e:
+        G.solve(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=2)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_timestepping_and_grids_match_oracle(G):
+    for dt, tspan, ns in [(0.01, (0, 1), 64), (0.01, (0, 0.4), 64), (1e-1, (0, 100), 256), (0.05, (0, 3300), 512),
+                          (np.float32(1e-3), (np.float32(0), np.float32(1)), 3), (4, (0, 200), 1)]:
+        a = G.resolve_fixed_timestepping(dt, tspan, ns)
+        b = O.resolve_fixed_timestepping(dt, tspan, ns)
+        assert a[0] == b[0] and a[2] == b[2] and a[1].dtype == b[1].dtype and a[1][0] == b[1][0]
+    for L, shape in [((8, 8), (16, 32)), ((np.float32(5), np.float32(7)), (8, 4)), ((20,), (64,)), ((3, 4, 5), (4, 8, 2))]:
+        u0 = (np.zeros(shape, dtype=np.complex128),)
+        pg, po = G.GrossPitaevskiiProblem(u0, L), O.GrossPitaevskiiProblem(u0, L)
+        for x, y in zip(G.direct_grid(pg), po.direct_grid()):
+            assert np.array_equal(x, y) and x.dtype == y.dtype
+        for x, y in zip(G.reciprocal_grid(pg), po.reciprocal_grid()):
+            assert np.array_equal(x, y) and x.dtype == y.dtype
+
+
+def _tables(ns, f, grid, param, dt, M):
+    from ggp_b200 import host
+    return host.exp_table(f, grid, param, dt, M)
+
+
+def test_exp_tables_match_oracle(G):
+    """get_exponential (src/misc.jl:12-20) on the host == the oracle's, for scalar / SVector / 2x2 SMatrix."""
+    pbg, pbo = P.exciton_polariton(G, N=16), P.exciton_polariton(O, N=16)
+    pg = G.GrossPitaevskiiProblem(pbg["u0"], pbg["lengths"], **pbg["kwargs"])
+    po = O.GrossPitaevskiiProblem(pbo["u0"], pbo["lengths"], **pbo["kwargs"])
+    dt = np.float64(0.09765625)
+    kind, tab = _tables(G, pg.dispersion, G.reciprocal_grid(pg), pg.param, dt, 2)
+    ref = O.get_exponential(po.dispersion, po.reciprocal_grid(), po.param, dt)
+    assert kind == G.lib.TABLE_FULL and tab.shape == (256, 4)
+    want = np.stack([ref[0, 0].ravel(), ref[1, 0].ravel(), ref[0, 1].ravel(), ref[1, 1].ravel()], axis=1)  # column-major
+    assert np.array_equal(tab, want)
+    # scalar + diag
+    disp = lambda ks, p: (ks[0] ** 2 + ks[1] ** 2) / 2 - 0.1j
+    kind, tab = _tables(G, disp, G.reciprocal_grid(pg), None, dt, 1)
+    assert kind == G.lib.TABLE_SCALAR and np.array_equal(tab[:, 0], O.get_exponential(disp, po.reciprocal_grid(), None, dt).ravel())
+    for mod in (G, O):
+        pass
+    dg = lambda ks, p: G.SVector(ks[0] ** 2, ks[1] - 0.2j)
+    do = lambda ks, p: O.SVector(ks[0] ** 2, ks[1] - 0.2j)
+    kind, tab = _tables(G, dg, G.reciprocal_grid(pg), None, dt, 2)
+    ref = O.get_exponential(do, po.reciprocal_grid(), None, dt)
+    assert kind == G.lib.TABLE_DIAG and np.array_equal(tab[:, 0], ref[0].ravel()) and np.array_equal(tab[:, 1], ref[1].ravel())
+
+
+def test_closure_recognition(G):
+    from ggp_b200 import host
+    from types import SimpleNamespace
+    # every nonlinearity of test/ and examples/ 
+    sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * G.abs2(u[0]), SimpleNamespace(g=-6), 1)
+    assert sc and c[0] == 0 and np.isclose(g[0, 0], -6)
+    sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * (G.abs2(u[0]) - 1 / p.dx), SimpleNamespace(g=3e-4, dx=2.0), 1)
+    assert np.isclose(c[0], -1.5e-4) and np.isclose(g[0, 0], 3e-4)
+    sc, c, g = host.recognise_nonlinearity(lambda u, p: G.SVector(0, p.g * G.abs2(u[1])), SimpleNamespace(g=0.015), 2)
+    assert not sc and np.allclose(c, 0) and np.allclose(g, [[0, 0], [0, 0.015]])
+    sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * G.abs2(u) / 2, SimpleNamespace(g=0.7), 1)
+    assert np.isclose(g[0, 0], 0.35)
+    with pytest.raises(G.UnsupportedForm):
+        host.recognise_nonlinearity(lambda u, p: G.abs2(u[0]) ** 2, None, 1)
+    with pytest.raises(G.UnsupportedForm):
+        host.recognise_nonlinearity(lambda u, p: np.real(u[0]), None, 1)   # phase dependent
+    # pump: separable time-dependent (bistability), static (EP), constant (TW)
+    pb = P.bistability(G, nsaves=4, tspan=(0, 25.78125))
+    prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    times = np.linspace(0.1, 25, 7)
+    pm = host.PumpModel(prob.pump, prob, (0.0, 25.78125), times)
+    pts = host._mesh(G.direct_grid(prob))
+    for t in (0.0, 3.0, 17.5):
+        F = np.broadcast_to(np.asarray(prob.pump(pts, prob.param, t), dtype=complex), (256,))
+        assert np.allclose(pm.amp(t) * pm.S[:, 0], F, rtol=1e-13, atol=1e-16)
+    bad = lambda x, p, t: np.exp(-(x[0] - t) ** 2)           # travelling pump: not separable
+    prob_bad = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], dispersion=prob.dispersion, pump=bad)
+    with pytest.raises(G.UnsupportedForm):
+        host.PumpModel(bad, prob_bad, (0.0, 10.0), times)
+    # noise: constant scalar ok, field dependent rejected
+    pbw = P.windowed_ft(G, ntraj=4)
+    probw = G.GrossPitaevskiiProblem(pbw["u0"], pbw["lengths"], **pbw["kwargs"])
+    eta = host.recognise_noise(probw.position_noise_func, probw)
+    assert np.isclose(eta[0], np.sqrt(probw.param.gamma / 2 / probw.param.dL))
+    with pytest.raises(G.UnsupportedForm):
+        host.recognise_noise(lambda u, r, p: abs(u[0]), probw)
+
+
+def test_pump_schedule_matches_oracle_times(G):
+    """The amplitude schedule handed to ggp_step is evaluated at the reference's times."""
+    t0, tt = O.pump_times((0, 3300 * 4 / 512), 0.05, 4)
+    dt, ts, sps = G.resolve_fixed_timestepping(0.05, (0, 3300 * 4 / 512), 4)
+    t = ts[0]
+    mine = []
+    for _ in range(4 * sps):
+        t = t + dt
+        mine.append((t + dt / 2, t + dt))
+    assert np.array_equal(np.array(mine), tt)
