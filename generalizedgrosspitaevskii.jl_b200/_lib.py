@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggp.so")
 
-GGP_ABI_VERSION = 1
+GGP_ABI_VERSION = 2
 GGP_C64, GGP_C128 = 0, 1
 TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL = 0, 1, 2, 3
 NL_NONE, NL_DIAG = 0, 1
@@ -21,7 +21,7 @@ EXPORTS = [
     "ggp_set_state", "ggp_get_state", "ggp_step", "ggp_synchronize", "ggp_observe",
     "ggp_comm_unique_id", "ggp_comm_init", "ggp_state_device_ptr", "ggp_timer_begin", "ggp_timer_end",
     "ggp_launch_count", "ggp_host_alloc", "ggp_host_free", "ggp_device_bytes", "ggp_profile_enable",
-    "ggp_profile_read", "ggp_debug_l2_flush",
+    "ggp_profile_read", "ggp_debug_l2_flush", "ggp_debug_flush_only",
 ]
 
 
@@ -43,6 +43,7 @@ class GgpDesc(C.Structure):
         ("pump_table", C.c_void_p), ("pump_amp0", C.c_double * 2),
         ("noise_kind", C.c_int32), ("noise_real", C.c_int32),
         ("noise_eta", (C.c_double * 2) * 2), ("seed", C.c_uint64),
+        ("slab_nranks", C.c_int32), ("slab_rank", C.c_int32),
     ]
 
 
@@ -91,6 +92,7 @@ def load():
     lib.ggp_host_free.argtypes = [vp]
     lib.ggp_profile_enable.argtypes = [vp, C.c_int]
     lib.ggp_debug_l2_flush.argtypes = [vp, C.c_uint64]
+    lib.ggp_debug_flush_only.argtypes = [vp, i64, C.POINTER(C.c_float)]
     lib.ggp_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     _lib = lib
     return lib

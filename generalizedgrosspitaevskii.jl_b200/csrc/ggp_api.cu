@@ -228,6 +228,14 @@ struct PlanT : PlanBase {
   double* obs_dev = nullptr;
   cpx<T>* scratch[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
+  // 3-D slab decomposition (one process per GPU): this rank holds z-planes [prank*n3loc, (prank+1)*n3loc) of the
+  // global (n1, n2, n3g) grid; for the z pass the data is transposed (NCCL all-to-all) into y-slabs
+  // (n1, n2loc, n3g) held in xbuf.  sendbuf stages the strided pack / unpack.
+  bool slab = false;
+  int P = 1, prank = 0;
+  long long n2g = 1, n3g = 1, n2loc = 1, n3loc = 1;
+  cpx<T>* xbuf[2] = {nullptr, nullptr};
+  cpx<T>* sendbuf[2] = {nullptr, nullptr};
   // TMA path of the strided kernel, per strided axis (1, 2)
   bool tma_ok[3] = {false, false, false};
   bool tma_d[3] = {false, false, false};  // exp_D staged by TMA as well
@@ -286,7 +294,7 @@ struct PlanT : PlanBase {
   // Checked numerically on the host table; if it holds the strided kernel never reads the full table.
   int detect_separable(const ggp_desc& d) {
     if (dkind != GGP_TABLE_SCALAR || ndim < 2 || getenv("GGP_NO_SEP")) return 0;
-    const long long nl = n[ndim - 1], np = nspatial / nl;
+    const long long nl = slab ? n3g : n[ndim - 1], np = nspatial / nl;
     std::vector<std::complex<double>> tab((size_t)nspatial);
     if (d.table_precision == GGP_C128) {
       memcpy(tab.data(), d.disp_table, sizeof(std::complex<double>) * (size_t)nspatial);
@@ -314,7 +322,7 @@ struct PlanT : PlanBase {
     if (const char* e = getenv("GGP_SEP_TOL")) tol = atof(e);
     if (!(emax <= tol * dmax)) return 0;
     std::vector<cpx<T>> hp((size_t)np), hl((size_t)nl);
-    const double sc = 1.0 / (double)nspatial;
+    const double sc = 1.0 / ((double)nspatial * P);
     for (long long q = 0; q < np; ++q) hp[(size_t)q] = mk<T>((T)(perp[(size_t)q].real() * sc), (T)(perp[(size_t)q].imag() * sc));
     for (long long l = 0; l < nl; ++l) hl[(size_t)l] = mk<T>((T)line[(size_t)l].real(), (T)line[(size_t)l].imag());
     int rc;
@@ -343,6 +351,22 @@ struct PlanT : PlanBase {
     batch_offset = d.batch_offset;
     dt = d.dt;
     dkind = d.disp_kind;
+    if (d.slab_nranks > 1) {
+      if (ndim != 3 || nbatch != 1) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid without batch dims");
+      if (d.noise_kind != GGP_NOISE_NONE) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition with noise is not supported yet");
+      P = d.slab_nranks;
+      prank = d.slab_rank;
+      if (prank < 0 || prank >= P || n[1] % P || n[2] % P) return fail(GGP_ERR_INVALID, "slab: n2 and n3 must be divisible by the number of ranks");
+      slab = true;
+      n2g = n[1];
+      n3g = n[2];
+      n2loc = n2g / P;
+      n3loc = n3g / P;
+      for (int i = 0; i < 3; ++i)
+        if (!size_supported(n[i])) return fail(GGP_ERR_UNSUPPORTED, "slab: axis lengths must be supported powers of two");
+      n[2] = n3loc;            // the resident layout is the z-slab (n1, n2, n3loc)
+      nspatial = n[0] * n[1] * n3loc;
+    }
     if (dkind != GGP_TABLE_NONE)
       for (int i = 0; i < ndim; ++i)
         if (!size_supported(n[i]))
@@ -367,23 +391,32 @@ struct PlanT : PlanBase {
       if (rc) return rc;
       GGP_CUDA(cudaMemsetAsync(u[c], 0, bytes, stream));
     }
+    if (slab) {
+      for (int c = 0; c < M; ++c) {
+        int rc2;
+        if ((rc2 = dalloc((void**)&xbuf[c], bytes))) return rc2;
+        if ((rc2 = dalloc((void**)&sendbuf[c], bytes))) return rc2;
+      }
+    }
     // tables.  The inverse transform is unnormalised on the device; the reference's 1/prod(n)
     // (ScaledPlan, src/misc.jl:56) is folded into exp_D -- exact for power-of-two sizes.
     int rc;
     if (dkind != GGP_TABLE_NONE) {
       if (!d.disp_table) return fail(GGP_ERR_INVALID, "disp_table is NULL");
-      if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / (double)nspatial, D))) return rc;
+      // (slab: the table arrives in the y-slab layout (n1, n2loc, n3g); same number of points as the z-slab)
+      if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / ((double)nspatial * P), D))) return rc;
       if ((rc = detect_separable(d))) return rc;
     }
     {
       for (int a = 0; a < ndim; ++a) {
+        const long long na = (slab && a == 2) ? n3g : n[a];
         for (int b = 0; b < a; ++b)
-          if (n[b] == n[a]) tw[a] = tw[b];
+          if (n[b] == na) tw[a] = tw[b];
         if (tw[a]) continue;
         // per-pass coalesced layout, see fft_line.cuh
         std::vector<cpx<T>> h;
         {
-          const long long N = n[a];
+          const long long N = na;
           const long long E = default_E<T>((int)N);
           const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
           for (long long NS = 1; NS < N;) {
@@ -461,7 +494,7 @@ struct PlanT : PlanBase {
     sm_count = prop.multiProcessorCount;
     // The TMA-fed persistent variant is opt-in (GGP_TMA=1): with 32-byte box rows (W = 4 complex64) it
     // measured slower than the LDG variant at two CTAs per SM on C2 (profiles/r01_notes.md).
-    if (!getenv("GGP_TMA") || getenv("GGP_NO_TMA")) return 0;
+    if (!getenv("GGP_TMA") || getenv("GGP_NO_TMA") || slab) return 0;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -580,12 +613,13 @@ struct PlanT : PlanBase {
     return prof_end();
   }
 
-  // strided pass along axis `ax` (1 or 2)
-  int run_str(int ax, int mode) {
+  // strided pass along axis `ax` (1 or 2).  yslab: operate on xbuf in the transposed (n1, n2loc, n3g) layout.
+  int run_str(int ax, int mode, bool yslab = false) {
     StrParams<T> p;
     memset(&p, 0, sizeof(p));
-    p.u[0] = u[0];
-    p.u[1] = u[1];
+    const long long g0 = n[0], g1 = yslab ? n2loc : n[1], g2 = yslab ? n3g : n[2];
+    p.u[0] = yslab ? xbuf[0] : u[0];
+    p.u[1] = yslab ? xbuf[1] : u[1];
     p.tw = tw[ax];
     for (int i = 0; i < 4; ++i) p.D[i] = D[i];
     p.dkind = dkind;
@@ -597,23 +631,24 @@ struct PlanT : PlanBase {
     p.mode = mode;
     long long nother;
     if (ax == 1) {
-      p.ls = n[0];
-      p.no1 = n[2];
-      p.s1 = n[0] * n[1];
+      p.ls = g0;
+      p.no1 = g2;
+      p.s1 = g0 * g1;
       p.s2 = nspatial;
-      p.ts1 = n[0] * n[1];
-      nother = n[2] * nbatch;
+      p.ts1 = g0 * g1;
+      nother = g2 * nbatch;
     } else {
-      p.ls = n[0] * n[1];
-      p.no1 = n[1];
-      p.s1 = n[0];
+      p.ls = g0 * g1;
+      p.no1 = g1;
+      p.s1 = g0;
       p.s2 = nspatial;
-      p.ts1 = n[0];
-      nother = n[1] * nbatch;
+      p.ts1 = g0;
+      nother = g1 * nbatch;
     }
+    const int N = (int)(ax == 1 ? g1 : g2);
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
-    if (tma_ok[ax]) {
+    if (tma_ok[ax] && !slab) {
       StrTmaParams<T> q;
       memset(&q, 0, sizeof(q));
       for (int c = 0; c < M; ++c) q.map[c] = tmap[ax][c];
@@ -632,13 +667,56 @@ struct PlanT : PlanBase {
       q.nplanes = ncols_of(dkind, M);
       q.stage_d = (mode == 1 && tma_d[ax] && p.dkind != KIND_SEP) ? 1 : 0;
       for (int i = 0; i < 4; ++i) q.dmap[i] = dmap[ax][i];
-      GGP_LAUNCH(dispatch_str_tma<T>((int)n[ax], M, q, n[0], nother, sm_count, stream), "str_tma_kernel");
+      GGP_LAUNCH(dispatch_str_tma<T>(N, M, q, g0, nother, sm_count, stream), "str_tma_kernel");
       ++launches;
       return prof_end();
     }
-    GGP_LAUNCH(dispatch_str<T>((int)n[ax], M, p, n[0], nother, stream), "str_kernel");
+    GGP_LAUNCH(dispatch_str<T>(N, M, p, g0, nother, stream), "str_kernel");
     ++launches;
     return prof_end();
+  }
+
+  // All-to-all transposes of the slab decomposition (ncclSend/ncclRecv group on the plan's stream).
+  // forward: z-slabs u (n1, n2g, n3loc) -> y-slabs xbuf (n1, n2loc, n3g);  backward: the inverse.
+  int transpose(bool forward) {
+#ifdef GGP_WITH_NCCL
+    if (!comm) return fail(GGP_ERR_NCCL, "slab plan without communicator: call ggp_comm_init first");
+    const size_t esz = sizeof(cpx<T>);
+    const long long blk = n[0] * n2loc * n3loc;                  // elements exchanged with each peer
+    const size_t width = (size_t)(n[0] * n2loc) * esz;           // one (x, y-range) chunk
+    const size_t zpitch = (size_t)(n[0] * n2g) * esz;            // one z-plane of the z-slab
+    const ncclDataType_t ty = sizeof(T) == 4 ? ncclFloat : ncclDouble;
+    for (int c = 0; c < M; ++c) {
+      if (forward) {
+        for (int q = 0; q < P; ++q)  // pack: peer q gets my z-planes restricted to its y-range
+          GGP_CUDA(cudaMemcpy2DAsync(sendbuf[c] + (size_t)q * blk, width, u[c] + (size_t)q * n[0] * n2loc, zpitch, width,
+                                     (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
+        ncclGroupStart();
+        for (int q = 0; q < P; ++q) {
+          ncclSend(sendbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);
+          ncclRecv(xbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);   // lands in place: z slowest
+        }
+        ncclResult_t r = ncclGroupEnd();
+        if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("all-to-all: ") + ncclGetErrorString(r));
+      } else {
+        ncclGroupStart();
+        for (int q = 0; q < P; ++q) {
+          ncclSend(xbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);    // contiguous: peer q's z-range
+          ncclRecv(sendbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);
+        }
+        ncclResult_t r = ncclGroupEnd();
+        if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("all-to-all: ") + ncclGetErrorString(r));
+        for (int q = 0; q < P; ++q)  // unpack: peer q's y-range of my z-planes
+          GGP_CUDA(cudaMemcpy2DAsync(u[c] + (size_t)q * n[0] * n2loc, zpitch, sendbuf[c] + (size_t)q * blk, width, width,
+                                     (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
+      }
+    }
+    launches += 0;
+    return 0;
+#else
+    (void)forward;
+    return fail(GGP_ERR_NCCL, "libggp was built without NCCL");
+#endif
   }
 
   // which compile-time variant of the half-step covers this problem (pointwise.cuh)
@@ -723,9 +801,15 @@ struct PlanT : PlanBase {
       amp_prev = a2;
       if (ndim == 2) {
         if ((rc = run_str(1, 1))) return rc;
-      } else {
+      } else if (!slab) {
         if ((rc = run_str(1, 0))) return rc;
         if ((rc = run_str(2, 1))) return rc;
+        if ((rc = run_str(1, 2))) return rc;
+      } else {
+        if ((rc = run_str(1, 0))) return rc;
+        if ((rc = transpose(true))) return rc;
+        if ((rc = run_str(2, 1, true))) return rc;
+        if ((rc = transpose(false))) return rc;
         if ((rc = run_str(1, 2))) return rc;
       }
     }
@@ -755,6 +839,7 @@ struct PlanT : PlanBase {
     } else if (kind == GGP_OBS_MOMENTUM) {
       // n(k) = sum_traj |fft(u)(k)|^2 / N^2 (examples/truncated_wigner.jl:110-113): transform the state in
       // place with the step's own FFT kernels, accumulate, then restore the saved copy.
+      if (slab) return fail(GGP_ERR_UNSUPPORTED, "momentum observable is not wired for slab-decomposed plans yet");
       for (int i = 0; i < ndim; ++i)
         if (!size_supported(n[i])) return fail(GGP_ERR_UNSUPPORTED, "momentum observable needs power-of-two axes");
       const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
@@ -818,6 +903,7 @@ int ggp_plan_create(const ggp_desc* d, ggp_plan** out) {
   if (!d || !out) return fail(GGP_ERR_INVALID, "null argument");
   *out = nullptr;
   if (d->abi_version != GGP_ABI_VERSION) return fail(GGP_ERR_INVALID, "abi_version mismatch");
+  if (d->slab_nranks < 0 || d->slab_nranks == 1) { /* 0 or 1: no slab decomposition */ }
   if (d->struct_size != sizeof(ggp_desc)) return fail(GGP_ERR_INVALID, "struct_size mismatch");
   if (d->ndim < 1 || d->ndim > 3) return fail(GGP_ERR_INVALID, "ndim must be 1..3");
   if (d->ncomp < 1 || d->ncomp > 2) return fail(GGP_ERR_UNSUPPORTED, "ncomp must be 1 or 2");
@@ -956,6 +1042,18 @@ int ggp_debug_l2_flush(ggp_plan* p, uint64_t bytes) {
     GGP_CUDA(cudaMalloc(&p->impl->flush_buf, bytes));
     p->impl->flush_bytes = bytes;
   }
+  return 0;
+}
+
+int ggp_debug_flush_only(ggp_plan* p, int64_t count, float* ms) {
+  GGP_ENTER(p);
+  if (!p->impl->flush_buf) return fail(GGP_ERR_INVALID, "ggp_debug_l2_flush is not enabled");
+  GGP_CUDA(cudaEventRecord(p->impl->ev0, p->impl->stream));
+  for (int64_t i = 0; i < count; ++i)
+    GGP_CUDA(cudaMemsetAsync(p->impl->flush_buf, 0, p->impl->flush_bytes, p->impl->stream));
+  GGP_CUDA(cudaEventRecord(p->impl->ev1, p->impl->stream));
+  GGP_CUDA(cudaEventSynchronize(p->impl->ev1));
+  GGP_CUDA(cudaEventElapsedTime(ms, p->impl->ev0, p->impl->ev1));
   return 0;
 }
 

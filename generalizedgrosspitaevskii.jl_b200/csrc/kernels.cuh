@@ -107,17 +107,44 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
                                            const HalfStep<T>* hs, const int nh, const long long sidx0,
                                            const long long gidx0, const long long stride) {
   constexpr int E = LineCfg<T, N>::E;
+  if constexpr (PWV == PW_STOCH) {
+    // All Philox words of this thread first (E*M independent chains: good ILP), one call per element and
+    // component serving both half-steps of the pair; then the half-steps as in the deterministic variant.
+    uint4 rnd[E][M];
+    if (pw.noise == NOISE_PHILOX) {
+      const uint32_t ctr_ref = hs[0].apply ? hs[0].ctr : hs[nh - 1].ctr;
+#pragma unroll
+      for (int m = 0; m < E; ++m)
+#pragma unroll
+        for (int c = 0; c < M; ++c)
+          rnd[m][c] = philox_for<T>(gidx0 + m * stride + pw.elem_offset, ctr_ref, c, pw.seed_lo, pw.seed_hi);
+    }
 #pragma unroll 1
-  for (int h = 0; h < nh; ++h) {
-    if (!hs[h].apply) continue;
+    for (int h = 0; h < nh; ++h) {
+      if (!hs[h].apply) continue;
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-      cpx<T> f[M];
+      for (int m = 0; m < E; ++m) {
+        cpx<T> f[M];
 #pragma unroll
-      for (int c = 0; c < M; ++c) f[c] = v[c][m];
-      half_step_point<T, M, PWV>(f, pw, hs[h], sidx0 + m * stride, gidx0 + m * stride);
+        for (int c = 0; c < M; ++c) f[c] = v[c][m];
+        half_step_point<T, M, PWV>(f, pw, hs[h], sidx0 + m * stride, gidx0 + m * stride, rnd[m]);
 #pragma unroll
-      for (int c = 0; c < M; ++c) v[c][m] = f[c];
+        for (int c = 0; c < M; ++c) v[c][m] = f[c];
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int h = 0; h < nh; ++h) {
+      if (!hs[h].apply) continue;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        cpx<T> f[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) f[c] = v[c][m];
+        half_step_point<T, M, PWV>(f, pw, hs[h], sidx0 + m * stride, gidx0 + m * stride, nullptr);
+#pragma unroll
+        for (int c = 0; c < M; ++c) v[c][m] = f[c];
+      }
     }
   }
 }
@@ -234,10 +261,12 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const One
 #pragma unroll
     for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
 
+  // half-step 0, then per step: [FFT x D x inverse FFT], then the trailing half-step of this step
+  // together with the leading half-step of the next one (they share one Philox call per element)
+  if (active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 1, t, goff, TPL);
 #pragma unroll 1
-  for (int hh = 0; hh < 2 * p.nsteps; ++hh) {
-    if (active) half_steps<T, N, M, PWV>(v, p.pw, p.hs + hh, 1, t, goff, TPL);
-    if ((hh & 1) == 0 && p.dkind != KIND_NONE) {
+  for (int st = 0; st < p.nsteps; ++st) {
+    if (p.dkind != KIND_NONE) {
 #pragma unroll 1
       for (int it = 0; it < 2; ++it) {
         fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 1);
@@ -254,6 +283,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const One
         }
       }
     }
+    if (active) half_steps<T, N, M, PWV>(v, p.pw, p.hs + 2 * st + 1, st + 1 < p.nsteps ? 2 : 1, t, goff, TPL);
   }
   if (active) {
 #pragma unroll

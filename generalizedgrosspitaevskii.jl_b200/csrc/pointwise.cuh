@@ -94,17 +94,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
-// xi with <|xi|^2> = 1 (complex prototype) or <xi^2> = 1 (real prototype), Box-Muller in fp32.
+// Noise stream.  One Philox call per (element, step pair, component) feeds BOTH half-steps that are
+// applied back to back around a step boundary: half-step counter c (0, 1, 2, ...) belongs to pair
+// (c+1)>>1 and uses words (x,y) if (c+1) is even, (z,w) otherwise -- the trailing half-step of step n and
+// the leading half-step of step n+1 (the two the fused kernels apply together) share a call.
+// The counter is the GLOBAL element index, so the stream does not depend on how trajectories are sharded.
 template <typename T>
-__device__ __forceinline__ cpx<T> philox_normal(long long gidx, uint32_t ctr, int comp, uint32_t k0, uint32_t k1,
-                                                int real_proto) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), ctr,
-                                           (uint32_t)comp), k0, k1);
-  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
-  const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+__device__ __forceinline__ uint4 philox_for(long long gidx, uint32_t ctr, int comp, uint32_t k0, uint32_t k1) {
+  return philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), (ctr + 1u) >> 1,
+                                  (uint32_t)comp), k0, k1);
+}
+
+// xi with <|xi|^2> = 1 (complex prototype) or <xi^2> = 1 (real prototype): Box-Muller in fp32 with the
+// fast MUFU paths (|error| ~ 1e-6, irrelevant for a random sample; the exact-parity route for stochastic
+// runs is the host-fed buffer).
+template <typename T>
+__device__ __forceinline__ cpx<T> normal_from(const uint4 r, uint32_t ctr, int real_proto) {
+  const bool second = ((ctr + 1u) & 1u) != 0;
+  const uint32_t w0 = second ? r.z : r.x, w1 = second ? r.w : r.y;
+  const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+  const float u2 = ((float)(w1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  const float l = -logf(u1);
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  const float l = -__logf(u1);
   if (real_proto) {
     const float rad = sqrtf(2.0f * l);
     return mk<T>((T)(rad * c), (T)0);
@@ -125,7 +137,7 @@ enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2 };
 // element index (spatial + batch) for noise.
 template <typename T, int M, int PWV>
 __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseParams<T>& p, const HalfStep<T>& h,
-                                                const long long sidx, const long long gidx) {
+                                                const long long sidx, const long long gidx, const uint4* rnd) {
   if constexpr (PWV == PW_KERR) {
     T n2[M];
 #pragma unroll
@@ -206,7 +218,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
       if (p.noise == NOISE_HOST) {
         xi = p.noise_real ? mk<T>(((const T*)h.xi[i])[gidx], (T)0) : ((const cpx<T>*)h.xi[i])[gidx];
       } else {
-        xi = philox_normal<T>(gidx + p.elem_offset, h.ctr, i, p.seed_lo, p.seed_hi, p.noise_real);
+        xi = normal_from<T>(rnd[i], h.ctr, p.noise_real);
       }
       // -i sqrt(dt) eta xi
       const cpx<T> ex = cmul(p.eta[i], xi);

@@ -335,8 +335,8 @@ def recognise_nonlinearity(f, param, M, rng=None):
 class PumpModel:
     """F_i(r, t) = S_i(r) a(t): S table (npoints, ncomp) and an amplitude function a(t)."""
 
-    def __init__(self, f, prob, tspan, times):
-        grid = direct_grid(prob)
+    def __init__(self, f, prob, tspan, times, grid=None):
+        grid = grid if grid is not None else direct_grid(prob)
         pts = _mesh(grid)
         shape = tuple(len(g) for g in reversed(grid))
         self.f, self.param, self.M = f, prob.param, len(prob.u0)
@@ -431,7 +431,11 @@ def _ptr_array(arrs):
 
 class StrangSplittingIterator:
     def __init__(self, prob, tspan, *, dt, nsaves, save_start=True, rng=None, device=-1,
-                 batch_offset=0, stream=None):
+                 batch_offset=0, stream=None, slab=None, slab_local=False):
+        """slab=(rank, world): 3-D slab decomposition, one process per GPU.  `prob.u0` is the GLOBAL field
+        (each rank keeps z-planes [rank*n3/world, (rank+1)*n3/world)), or already this rank's z-slab if
+        slab_local=True.  Results / fetch() are the local z-slab.  Attach a communicator
+        (parallel.attach_nccl) before stepping."""
         lib = L.load()
         self.lib = lib
         self.prob = prob
@@ -445,11 +449,37 @@ class StrangSplittingIterator:
             raise ValueError("fields must be ComplexF32 or ComplexF64")
         self.dtype = dtype
         sizes = prob.sizes
-        nspatial = int(np.prod(sizes))
-        self.nbatch = int(prob.u0[0].size // nspatial)
-        self.result = tuple(np.stack([x] * (nsaves + self.save_start), axis=0) for x in prob.u0)  # :41-43
+        u0_local = prob.u0
+        self.slab = slab
+        dg_pump = None
+        if slab is not None:
+            rank, world = slab
+            if prob.ndim != 3 or prob.u0[0].ndim != 3:
+                raise ValueError("slab decomposition needs a 3-D problem without batch dims")
+            if slab_local:                                   # u0 is this rank's z-slab: rebuild the global sizes
+                sizes = (sizes[0], sizes[1], sizes[2] * world)
+                gshape = (sizes[2], sizes[1], sizes[0])
+                prob_g = GrossPitaevskiiProblem(tuple(np.broadcast_to(np.zeros((), dtype), gshape) for _ in prob.u0),
+                                                prob.lengths)
+            else:
+                prob_g = prob
+            n3l, n2l = sizes[2] // world, sizes[1] // world
+            z0, y0 = rank * n3l, rank * n2l
+            if not slab_local:
+                u0_local = tuple(np.ascontiguousarray(x[z0:z0 + n3l]) for x in prob.u0)
+            rg_g, dg_g = reciprocal_grid(prob_g), direct_grid(prob_g)
+            rg = (rg_g[0], rg_g[1][y0:y0 + n2l], rg_g[2])     # y-slab: the layout of the z pass
+            dg = (dg_g[0], dg_g[1], dg_g[2][z0:z0 + n3l])     # z-slab: the resident layout
+            dg_pump = dg
+            nspatial = int(np.prod(sizes)) // world
+            self.nbatch = 1
+        else:
+            nspatial = int(np.prod(sizes))
+            self.nbatch = int(prob.u0[0].size // nspatial)
+            rg, dg = reciprocal_grid(prob), direct_grid(prob)
+        self.u0_local = u0_local
+        self.result = tuple(np.stack([x] * (nsaves + self.save_start), axis=0) for x in u0_local)  # :41-43
 
-        rg, dg = reciprocal_grid(prob), direct_grid(prob)
         dkind, dtab = exp_table(prob.dispersion, rg, prob.param, self.dt, M)            # :53
         vkind, vtab = exp_table(prob.potential, dg, prob.param, self.dt / 2, M)         # :54
 
@@ -464,6 +494,8 @@ class StrangSplittingIterator:
         d.device = device
         d.stream = stream
         d.dt = float(self.dt)
+        if slab is not None:
+            d.slab_rank, d.slab_nranks = int(slab[0]), int(slab[1])
         keep = []
 
         def as_c128(t):
@@ -495,7 +527,7 @@ class StrangSplittingIterator:
                 t = t + self.dt
                 times[i, 0] = t + self.dt / 2
                 times[i, 1] = t + self.dt
-            pm = PumpModel(prob.pump, prob, (self.ts[0], _jl(tspan[-1])), times.reshape(-1))
+            pm = PumpModel(prob.pump, prob, (self.ts[0], _jl(tspan[-1])), times.reshape(-1), grid=dg_pump)
             self.pump_model = pm
             d.pump_kind, d.pump_ncomp = L.PUMP_SEPARABLE, pm.ncomp
             d.pump_table = as_c128(pm.S)
@@ -531,8 +563,8 @@ class StrangSplittingIterator:
         L.check(lib.ggp_plan_create(C.byref(d), C.byref(handle)))
         self.handle = handle
         self._pinned = []
-        self.u = [self._pinned_like(x) for x in prob.u0]                                # :48 (pinned staging)
-        for dst, src in zip(self.u, prob.u0):
+        self.u = [self._pinned_like(x) for x in u0_local]                               # :48 (pinned staging)
+        for dst, src in zip(self.u, u0_local):
             np.copyto(dst, src)
         L.check(lib.ggp_set_state(self.handle, _ptr_array(self.u)))
         self._step_index = 0
@@ -592,13 +624,14 @@ class StrangSplittingIterator:
         return self.u
 
     def observe(self, kind):
-        nspatial = int(np.prod(self.prob.sizes))
+        shape = self.u[0].shape[self.u[0].ndim - self.prob.ndim:]
+        nspatial = int(np.prod(shape))
         n = self.M if kind == L.OBS_NORM else self.M * nspatial
         out = np.empty(n, dtype=np.float64)
         L.check(self.lib.ggp_observe(self.handle, kind, out.ctypes.data))
         if kind == L.OBS_NORM:
             return out
-        return out.reshape((self.M,) + tuple(reversed(self.prob.sizes)))
+        return out.reshape((self.M,) + tuple(shape))
 
 
 def init(prob, alg, tspan, *, dt, nsaves, show_progress=True, progress=None, save_start=True,

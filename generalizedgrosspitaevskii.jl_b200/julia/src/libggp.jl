@@ -6,7 +6,7 @@
 # mirror (../host.py) implements the same logic line for line and IS exercised by the test-suite.
 using Libdl
 
-const GGP_ABI_VERSION = UInt32(1)
+const GGP_ABI_VERSION = UInt32(2)
 const GGP_C64, GGP_C128 = Int32(0), Int32(1)
 const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL = Int32(0), Int32(1), Int32(2), Int32(3)
 
@@ -42,6 +42,8 @@ struct GgpDesc
     noise_real::Int32
     noise_eta::NTuple{4,Float64}
     seed::UInt64
+    slab_nranks::Int32           # 3-D slab decomposition (0/1 = off), see include/ggp.h
+    slab_rank::Int32
 end
 
 const _lib = Ref{Ptr{Cvoid}}(C_NULL)

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGP_ABI_VERSION 1u
+#define GGP_ABI_VERSION 2u
 
 typedef enum ggp_status {
   GGP_OK = 0,
@@ -127,6 +127,14 @@ typedef struct ggp_desc {
   int32_t noise_real;   /* 1: noise_prototype is a real array (xi ~ N(0,1)); 0: complex (<|xi|^2> = 1) */
   double noise_eta[2][2]; /* eta_i [i][re/im]; if the closure returned a Number, repeat it */
   uint64_t seed;        /* Philox4x32-10 key */
+
+  /* 3-D slab decomposition over slab_nranks processes (one per GPU), 0 or 1 = off.  n[] stays the GLOBAL
+     grid; this rank's state is the z-slab n[0] x n[1] x (n[2]/slab_nranks) starting at plane
+     slab_rank*n[2]/slab_nranks; pot_table / pump_table cover that z-slab; disp_table covers the y-slab
+     n[0] x (n[1]/slab_nranks) x n[2] starting at row slab_rank*n[1]/slab_nranks (the layout after the
+     all-to-all transpose, in which the z lines are local).  Needs ggp_comm_init before ggp_step. */
+  int32_t slab_nranks;
+  int32_t slab_rank;
 } ggp_desc;
 
 typedef struct ggp_plan ggp_plan;
@@ -184,6 +192,8 @@ int ggp_profile_enable(ggp_plan *plan, int on);
    that each kernel starts with a cold L2 (timing rule for working sets smaller than the 126 MB L2).
    The flushes are outside the per-kernel events of ggp_profile_read.  bytes = 0 switches it off. */
 int ggp_debug_l2_flush(ggp_plan *plan, uint64_t bytes);
+/* Time `count` of those flushes alone (same stream, one event pair): subtracted from a bracketed flushed run. */
+int ggp_debug_flush_only(ggp_plan *plan, int64_t count, float *milliseconds);
 int ggp_profile_read(ggp_plan *plan, double *ms_total, int64_t *launches);
 
 #ifdef __cplusplus

@@ -149,7 +149,8 @@ def windowed_ft(ns, ntraj=10 ** 4, N=64):
                 tspan=(0, 200), dt=dt, nsaves=1, save_start=False, L=L, N=N)
 
 
-def truncated_wigner(ns, ntraj=256, N=256, ndim=1, dtype=np.complex128, seed=1234, tspan=(0, 200), dt=0.05):
+def truncated_wigner(ns, ntraj=256, N=256, ndim=1, dtype=np.complex128, seed=1234, tspan=(0, 200), dt=0.05,
+                     traj_range=None):
     """examples/truncated_wigner.jl:33-50,93-99 (1-D as shipped; ndim=2 is BASELINE config C4)."""
     hbar = 0.6582
     gamma = 0.047 / hbar
@@ -174,10 +175,18 @@ def truncated_wigner(ns, ntraj=256, N=256, ndim=1, dtype=np.complex128, seed=123
     def position_noise_func(psi, xs, p):
         return np.sqrt(p.gamma / (2 * p.dx))
 
-    rng = np.random.default_rng(seed)
-    shape = (ntraj,) + (N,) * ndim
-    z = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)
-    u0 = ((z / np.sqrt(2 * vol)).astype(dtype),)
+    # the ensemble is generated in blocks of 256 trajectories seeded by (seed, block), so that rank r of a
+    # sharded run can build exactly its slice [lo, hi) of the same global ensemble
+    lo, hi = traj_range if traj_range is not None else (0, ntraj)
+    B = 256
+    parts = []
+    for b in range(lo // B, (hi + B - 1) // B):
+        rng = np.random.default_rng([seed, b])
+        shape = (B,) + (N,) * ndim
+        z = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)
+        a, e = max(lo, b * B) - b * B, min(hi, (b + 1) * B) - b * B
+        parts.append((z[a:e] / np.sqrt(2 * vol)).astype(dtype))
+    u0 = (np.concatenate(parts, axis=0),)
     noise_prototype = tuple(np.empty_like(x) for x in u0)
     return dict(u0=u0, lengths=(L,) * ndim,
                 kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, pump=pump, param=param,

@@ -1,0 +1,97 @@
+"""3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2 GPUs, NCCL all-to-all transpose for
+the z pass, compared with the unsharded CPU oracle.  Needs >= 2 CUDA devices (gpurun --gpus 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _cases(ns):
+    import problems as P
+    out = []
+    for dtype in (np.complex128, np.complex64):
+        pb = P.kerr3d(ns, N=32, dtype=dtype, nsteps=6)
+        out.append(("kerr3d_%s" % np.dtype(dtype).name, pb))
+    # rectangular grid + scalar potential (z-slab table slicing) + non-separable dispersion (full table path)
+    rng = np.random.default_rng(3)
+    shape = (64, 32, 16)   # numpy (n3, n2, n1)
+    u0 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex128)
+
+    def disp(ks, p):
+        return (ks[0] ** 2 + ks[1] ** 2 + ks[2] ** 2) / 2 + 0.05 * ks[0] * ks[2]
+
+    def pot(r, p):
+        return 0.3 * (r[2] - 2.0) ** 2 + 0.1 * r[0] - 0.02j
+
+    def nl(u, p):
+        return 0.5 * ns.abs2(u[0])
+    out.append(("rect_potential", dict(u0=(u0,), lengths=(5.0, 7.0, 9.0),
+                                       kwargs=dict(dispersion=disp, potential=pot, nonlinearity=nl),
+                                       tspan=(0.0, 0.05), dt=0.01, nsaves=1)))
+    return out
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ggp_b200 as G
+    results = {}
+    for name, pb in _cases(G):
+        prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+        it = G.init(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"], device=rank,
+                    slab=(rank, world))
+        G.parallel.attach_nccl(G, it, dist)
+        ts, sol = G.solve_(it)
+        it.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, sol[0][-1])
+        results[name] = np.concatenate(gathered, axis=0)      # z-slabs stack along numpy axis 0
+    if rank == 0:
+        q.put(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_slab_decomposition_matches_oracle():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ggp_oracle as O
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for name, pb in _cases(O):
+        prob = O.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+        _, sol = O.solve(prob, O.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"])
+        ref = sol[0][-1].astype(np.complex128)
+        got = results[name].astype(np.complex128)
+        err = np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel())
+        tol = 1e-4 if sol[0].dtype == np.complex64 else 1e-10
+        assert err <= tol, (name, err)
