@@ -70,6 +70,14 @@ def make_workload(ns, name, nbatch=None, n=None, traj_range=None):
                                  "ComplexF64, in-kernel Philox noise (BASELINE.json configs[3])",
                         grid=[256, 256], ncomp=1, nbatch=nb, dtype="c128", points=256 * 256 * nb,
                         bytes_row=32, bytes_str=32, b_alg_contract=96)
+    if name == "c5":
+        N = n or 512
+        rank, world = traj_range if traj_range is not None else (0, 1)
+        pb = P.kerr3d_slab(ns, N=N, rank=rank, world=world, dtype=np.complex64)
+        return pb, dict(workload=f"C5: 3-D BEC Kerr GPE {N}^3 ComplexF32, slab-decomposed over {world} GPU(s) with an NCCL "
+                                 "all-to-all transpose (BASELINE.json configs[4]; 1024^3 with --grid 1024)",
+                        grid=[N, N, N], ncomp=1, nbatch=1, dtype="c64", points=N * N * N // world,
+                        bytes_row=16, bytes_str=16, b_alg_contract=88)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -186,17 +194,19 @@ def ncu_traffic(kernel_class, workload):
 
 
 def measure(G, name, steps, warmup, device, nbatch=None, batch_offset=0, do_e2e=True, do_flush=True, comm=None,
-            n=None):
+            n=None, slab=None):
     """Returns dict with chained / flushed / per-kernel / e2e numbers for one plan on this rank."""
     lib = G.lib.load()
     pb, meta = make_workload(G, name, nbatch=nbatch, n=n,
-                             traj_range=(batch_offset, batch_offset + nbatch) if (name == "c4" and nbatch) else None)
+                             traj_range=(slab if name == "c5" else
+                                         ((batch_offset, batch_offset + nbatch) if (name == "c4" and nbatch) else None)))
     prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
     nsaves_steps = steps + warmup + steps + steps + steps + 8
     dt = pb["dt"]
     tspan = (pb["tspan"][0], pb["tspan"][0] + type(dt)(4 * nsaves_steps) * dt)
+    skw = dict(slab=slab, slab_local=True) if (slab is not None and slab[1] > 1) else {}
     it = G.init(prob, G.StrangSplitting(), tspan, dt=dt, nsaves=1, save_start=False, rng=1234, device=device,
-                batch_offset=batch_offset)
+                batch_offset=batch_offset, **skw)
     if comm is not None:
         comm(it)
     h = it.handle
@@ -303,15 +313,32 @@ def allsum(x):
     return float(t.item())
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 (e.g. NCCL's
+    version banner) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
-    global _DIST
+    global _DIST, _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--n", type=int, default=None, help="grid edge override (size sweep)")
+    ap.add_argument("--grid", dest="n", type=int, default=None, help="grid edge override (size sweep)")
     ap.add_argument("--nbatch", type=int, default=4096, help="total trajectories of the c4 ensemble")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -342,7 +369,7 @@ def main():
                     cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -363,7 +390,12 @@ def main():
     # ---- headline workload ---------------------------------------------------------------------
     res = measure(G, a.workload, a.steps, a.warmup, local, n=a.n,
                   nbatch=(a.nbatch // world if a.workload == "c4" else None),
-                  batch_offset=(rank * (a.nbatch // world) if a.workload == "c4" else 0))
+                  batch_offset=(rank * (a.nbatch // world) if a.workload == "c4" else 0),
+                  slab=((rank, world) if a.workload == "c5" else None),
+                  comm=((lambda it: attach_comm(G, it, world, rank)) if (a.workload == "c5" and world > 1) else None),
+                  do_e2e=(a.workload != "c5"))
+    if "e2e" not in res:
+        res["e2e"] = dict(seconds=float("nan"), h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     meta = res["meta"]
     pts = meta["points"]
     chained_ms = allmax(res["chained_ms"])
@@ -396,7 +428,7 @@ def main():
     value_chained = total_pts * a.steps / (chained_ms * 1e-3)
     line = dict(metric=METRIC, value=value_cold, unit=METRIC, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=cold_ms / a.steps, higher_is_better=True,
-                scaling="strong" if a.workload == "c4" else "weak", vs_baseline=None, dtype=meta["dtype"],
+                scaling="strong" if a.workload in ("c4", "c5") else "weak", vs_baseline=None, dtype=meta["dtype"],
                 data="synthetic",
                 config=dict(workload=meta["workload"], grid=meta["grid"], ncomp=meta["ncomp"], nbatch=meta["nbatch"],
                             parallelism=("single GPU" if world == 1 else
@@ -448,6 +480,22 @@ def main():
             it4.close()
         except Exception as e:  # extras must never take the headline down
             extra["c4_ensemble"] = dict(error=repr(e))
+        if world > 1:
+            try:
+                k5 = 20
+                r5 = measure(G, "c5", k5, 3, local, n=512, slab=(rank, world), do_e2e=False, do_flush=False,
+                             comm=lambda it: attach_comm(G, it, world, rank))
+                ms5 = allmax(r5["chained_ms"])
+                pts5 = allsum(float(r5["meta"]["points"]))
+                extra["c5_slab"] = dict(workload=r5["meta"]["workload"], scaling="strong", value=pts5 * k5 / (ms5 * 1e-3),
+                                        unit=METRIC, ms_per_step=ms5 / k5, steps=k5,
+                                        per_kernel_ms=dict(row=r5["prof"]["ms"][0] / max(1, r5["prof"]["n"][0]),
+                                                           str_d=r5["prof"]["ms"][1] / max(1, r5["prof"]["n"][1]),
+                                                           str_fi=r5["prof"]["ms"][2] / max(1, r5["prof"]["n"][2])))
+                windows += r5["windows"]
+                r5["iter"].close()
+            except Exception as e:
+                extra["c5_slab"] = dict(error=repr(e))
         if world == 1:
             try:
                 r3 = measure(G, "c3", 200, 5, local, do_e2e=False, do_flush=False)
@@ -469,7 +517,7 @@ def main():
                 line["cpu_baseline"] = cb
             except Exception as e:
                 line["cpu_baseline"] = dict(value=None, unit=METRIC, cores=0, kind="port", sample=f"failed: {e!r}")
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         _DIST.barrier()
         _DIST.destroy_process_group()
@@ -488,6 +536,8 @@ def attach_comm(G, it, world, rank):
     raw = bytes(t.cpu().tolist())
     buf = C.create_string_buffer(raw, 128)
     G.lib.check(lib.ggp_comm_init(it.handle, world, rank, buf))
+    if it.slab is None:
+        it.observe(G.lib.OBS_NORM)      # warm-up collective: NCCL sets its channels up lazily on first use
 
 
 if __name__ == "__main__":

@@ -688,27 +688,36 @@ struct PlanT : PlanBase {
     const ncclDataType_t ty = sizeof(T) == 4 ? ncclFloat : ncclDouble;
     for (int c = 0; c < M; ++c) {
       if (forward) {
+        // my own block never touches NCCL: one strided copy u -> xbuf
+        GGP_CUDA(cudaMemcpy2DAsync(xbuf[c] + (size_t)prank * blk, width, u[c] + (size_t)prank * n[0] * n2loc, zpitch, width,
+                                   (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
         for (int q = 0; q < P; ++q)  // pack: peer q gets my z-planes restricted to its y-range
-          GGP_CUDA(cudaMemcpy2DAsync(sendbuf[c] + (size_t)q * blk, width, u[c] + (size_t)q * n[0] * n2loc, zpitch, width,
-                                     (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
+          if (q != prank)
+            GGP_CUDA(cudaMemcpy2DAsync(sendbuf[c] + (size_t)q * blk, width, u[c] + (size_t)q * n[0] * n2loc, zpitch, width,
+                                       (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
         ncclGroupStart();
         for (int q = 0; q < P; ++q) {
+          if (q == prank) continue;
           ncclSend(sendbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);
           ncclRecv(xbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);   // lands in place: z slowest
         }
         ncclResult_t r = ncclGroupEnd();
         if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("all-to-all: ") + ncclGetErrorString(r));
       } else {
+        GGP_CUDA(cudaMemcpy2DAsync(u[c] + (size_t)prank * n[0] * n2loc, zpitch, xbuf[c] + (size_t)prank * blk, width, width,
+                                   (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
         ncclGroupStart();
         for (int q = 0; q < P; ++q) {
+          if (q == prank) continue;
           ncclSend(xbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);    // contiguous: peer q's z-range
           ncclRecv(sendbuf[c] + (size_t)q * blk, (size_t)blk * 2, ty, q, comm, stream);
         }
         ncclResult_t r = ncclGroupEnd();
         if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("all-to-all: ") + ncclGetErrorString(r));
         for (int q = 0; q < P; ++q)  // unpack: peer q's y-range of my z-planes
-          GGP_CUDA(cudaMemcpy2DAsync(u[c] + (size_t)q * n[0] * n2loc, zpitch, sendbuf[c] + (size_t)q * blk, width, width,
-                                     (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
+          if (q != prank)
+            GGP_CUDA(cudaMemcpy2DAsync(u[c] + (size_t)q * n[0] * n2loc, zpitch, sendbuf[c] + (size_t)q * blk, width, width,
+                                       (size_t)n3loc, cudaMemcpyDeviceToDevice, stream));
       }
     }
     launches += 0;

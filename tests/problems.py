@@ -236,3 +236,32 @@ def kerr3d(ns, N=32, dtype=np.complex64, L=32.0, g=1.0, dt=1e-3, nsteps=10, seed
     return dict(u0=(u0,), lengths=(Lr, Lr, Lr),
                 kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=SimpleNamespace(g=real(g))),
                 tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=1)
+
+
+def kerr3d_slab(ns, N=512, rank=0, world=1, dtype=np.complex64, L=32.0, g=1.0, dt=1e-3, nsteps=100, seed=1234):
+    """BASELINE config C5 built slab by slab: rank's z-planes [rank*N/world, (rank+1)*N/world) of the
+    N^3 Gaussian + 1 % noise field; the noise is seeded per z-plane so every sharding sees the same global field."""
+    real = np.float32 if dtype == np.complex64 else np.float64
+    Lr = real(L)
+    rs = np.arange(N).astype(real) * (Lr / N)
+    nz = N // world
+    z0 = rank * nz
+    Y, X = np.meshgrid(rs, rs, indexing="ij")
+    gxy = np.exp(-((X - Lr / 2) ** 2 + (Y - Lr / 2) ** 2) / 16).astype(real)
+    u0 = np.empty((nz, N, N), dtype=dtype)
+    for k in range(nz):
+        rng = np.random.default_rng([seed, z0 + k])
+        xi = rng.standard_normal((N, N, 2), dtype=np.float32)
+        gz = real(np.exp(-((rs[z0 + k] - Lr / 2) ** 2) / 16))
+        u0[k] = (gxy * gz) * (1 + real(0.01 / np.sqrt(2)) * (xi[..., 0] + 1j * xi[..., 1]))
+
+    def dispersion(ks, param):
+        return _sumsq(ks) / 2
+
+    def nonlinearity(u, param):
+        return param.g * ns.abs2(u[0])
+
+    dtr = real(dt)
+    return dict(u0=(u0,), lengths=(Lr, Lr, Lr),
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=SimpleNamespace(g=real(g))),
+                tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=1)
