@@ -6,6 +6,57 @@
 
 namespace ggp {
 
+// f2: two fp32 values in one 64-bit register pair, operated on with Blackwell's packed fp32x2
+// instructions (add/sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2).  A cpx<f2> is TWO complex numbers
+// (lane 0 = line A, lane 1 = line B) that go through identical arithmetic: the FFT of two lines at
+// half the instruction-issue cost (the fp32 kernels are issue-bound, profiles/r01_notes.md).
+struct alignas(8) f2 {
+  float2 v;
+};
+__device__ __forceinline__ f2 mkf2(float a, float b) {
+  f2 r;
+  r.v = make_float2(a, b);
+  return r;
+}
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return f2{__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return f2{__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<f2*>(&r);
+}
+__device__ __forceinline__ f2 operator-(f2 a) { return mkf2(0.f, 0.f) - a; }
+
+// a*b + c and c - a*b for every arithmetic type (scalar types: the compiler contracts to FMA itself)
+__device__ __forceinline__ float fma_(float a, float b, float c) { return a * b + c; }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return a * b + c; }
+__device__ __forceinline__ f2 fma_(f2 a, f2 b, f2 c) { return f2{__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ float fnma_(float a, float b, float c) { return c - a * b; }
+__device__ __forceinline__ double fnma_(double a, double b, double c) { return c - a * b; }
+__device__ __forceinline__ f2 fnma_(f2 a, f2 b, f2 c) {  // c - a*b = fma(a, b, -c) negated ... kept as sub of a product
+  return c - a * b;
+}
+// compile-time constant of type T
+template <typename T>
+__device__ __forceinline__ T cst(double c) {
+  return (T)c;
+}
+template <>
+__device__ __forceinline__ f2 cst<f2>(double c) {
+  return mkf2((float)c, (float)c);
+}
+// scalar type behind T and number of lines it carries
+template <typename T>
+struct Lanes {
+  using scalar = T;
+  static constexpr int N = 1;
+};
+template <>
+struct Lanes<f2> {
+  using scalar = float;
+  static constexpr int N = 2;
+};
+
 template <typename T>
 struct alignas(2 * sizeof(T)) cpx {
   T x, y;
@@ -28,12 +79,12 @@ __device__ __forceinline__ cpx<T> operator-(cpx<T> a, cpx<T> b) {
 }
 template <typename T>
 __device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) {
-  return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return mk<T>(fnma_(a.y, b.y, a.x * b.x), fma_(a.y, b.x, a.x * b.y));
 }
 // a * conj(b)
 template <typename T>
 __device__ __forceinline__ cpx<T> cmulc(cpx<T> a, cpx<T> b) {
-  return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+  return mk<T>(fma_(a.y, b.y, a.x * b.x), fnma_(a.x, b.y, a.y * b.x));
 }
 template <typename T>
 __device__ __forceinline__ cpx<T> cscale(cpx<T> a, T s) {
@@ -41,7 +92,7 @@ __device__ __forceinline__ cpx<T> cscale(cpx<T> a, T s) {
 }
 template <typename T>
 __device__ __forceinline__ T cabs2(cpx<T> a) {
-  return a.x * a.x + a.y * a.y;
+  return fma_(a.y, a.y, a.x * a.x);
 }
 // multiply by  s*i  where s = DIR (DIR=-1: forward transform e^{-i..}, DIR=+1: inverse)
 template <typename T, int DIR>
@@ -91,26 +142,48 @@ struct Dft {
     Dft<T, H, DIR>::run(o);
 #pragma unroll
     for (int k = 0; k < H; ++k) {
-      cpx<T> t;
+      // v[k] = e + w^k o,  v[k+H] = e - w^k o,  w = exp(DIR*2*pi*i/R); the trivial rotations are written out
+      // so that no explicit negation is ever needed (a negation is a real instruction for the packed type)
+      const cpx<T> ek = e[k], ok = o[k];
       if (k == 0) {
-        t = o[k];
-      } else if (4 * k == R) {
-        t = mul_si<T, DIR>(o[k]);
-      } else if (8 * k == R) {  // (1 + s i)/sqrt2
-        const T h = (T)0.70710678118654752440;
-        t = DIR < 0 ? mk<T>((o[k].x + o[k].y) * h, (o[k].y - o[k].x) * h)
-                    : mk<T>((o[k].x - o[k].y) * h, (o[k].y + o[k].x) * h);
-      } else if (8 * k == 3 * R) {  // (-1 + s i)/sqrt2
-        const T h = (T)0.70710678118654752440;
-        t = DIR < 0 ? mk<T>((o[k].y - o[k].x) * h, -(o[k].x + o[k].y) * h)
-                    : mk<T>(-(o[k].x + o[k].y) * h, (o[k].x - o[k].y) * h);
+        v[k] = ek + ok;
+        v[k + H] = ek - ok;
+      } else if (4 * k == R) {  // w^k = DIR*i :  t = (-DIR*o.y, DIR*o.x)
+        if (DIR < 0) {
+          v[k] = mk<T>(ek.x + ok.y, ek.y - ok.x);
+          v[k + H] = mk<T>(ek.x - ok.y, ek.y + ok.x);
+        } else {
+          v[k] = mk<T>(ek.x - ok.y, ek.y + ok.x);
+          v[k + H] = mk<T>(ek.x + ok.y, ek.y - ok.x);
+        }
+      } else if (8 * k == R) {  // (1 + DIR*i)/sqrt2
+        const T h = cst<T>(0.70710678118654752440);
+        const T p = (ok.x + ok.y) * h, q = (ok.y - ok.x) * h;
+        if (DIR < 0) {  // t = (p, q)
+          v[k] = mk<T>(ek.x + p, ek.y + q);
+          v[k + H] = mk<T>(ek.x - p, ek.y - q);
+        } else {        // t = (-q, p)
+          v[k] = mk<T>(ek.x - q, ek.y + p);
+          v[k + H] = mk<T>(ek.x + q, ek.y - p);
+        }
+      } else if (8 * k == 3 * R) {  // (-1 + DIR*i)/sqrt2
+        const T h = cst<T>(0.70710678118654752440);
+        const T p = (ok.x + ok.y) * h, q = (ok.y - ok.x) * h;
+        if (DIR < 0) {  // t = (q, -p)
+          v[k] = mk<T>(ek.x + q, ek.y - p);
+          v[k + H] = mk<T>(ek.x - q, ek.y + p);
+        } else {        // t = (-p, -q)
+          v[k] = mk<T>(ek.x - p, ek.y - q);
+          v[k + H] = mk<T>(ek.x + p, ek.y + q);
+        }
       } else {
-        const T c = (T)cos32(k * (32 / R));
-        const T s = (T)(DIR * sin32(k * (32 / R)));
-        t = mk<T>(o[k].x * c - o[k].y * s, o[k].x * s + o[k].y * c);
+        const T c = cst<T>(cos32(k * (32 / R)));
+        const T sn = cst<T>(DIR * sin32(k * (32 / R)));
+        const T msn = cst<T>(-DIR * sin32(k * (32 / R)));
+        const cpx<T> t = mk<T>(fma_(ok.y, msn, ok.x * c), fma_(ok.y, c, ok.x * sn));
+        v[k] = ek + t;
+        v[k + H] = ek - t;
       }
-      v[k] = e[k] + t;
-      v[k + H] = e[k] - t;
     }
   }
 };

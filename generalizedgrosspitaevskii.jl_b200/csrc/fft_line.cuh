@@ -15,8 +15,16 @@ __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v
 // Elements per thread.  fp32: radix-16 passes (32 data registers); fp64: radix-8 (32 data
 // registers).  Long lines use a wider radix so that a line never needs more than 256 threads.
 template <typename T>
+struct IsPacked {
+  static constexpr bool value = false;
+};
+template <>
+struct IsPacked<f2> {
+  static constexpr bool value = true;
+};
+template <typename T>
 __host__ __device__ constexpr int default_E(int N) {
-  int e = sizeof(T) == 4 ? 16 : 8;
+  int e = (sizeof(T) == 4 || IsPacked<T>::value) ? 16 : 8;
   while (N / e > 256) e *= 2;
   return e < N ? e : N;
 }

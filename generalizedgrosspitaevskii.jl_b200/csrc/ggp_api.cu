@@ -10,7 +10,11 @@
 #include <vector>
 
 #include "../../include/ggp.h"
+#include <type_traits>
 #include "str_tma.cuh"
+#ifdef GGP_PACKED
+#include "packed.cuh"
+#endif
 #include "sizes_gen.h"
 
 #ifdef GGP_WITH_NCCL
@@ -108,6 +112,33 @@ static bool size_supported(long long n) {
   }
   return false;
 }
+
+#ifdef GGP_PACKED
+// packed two-line fp32 kernels (packed.cuh): line lengths >= GGP_PACKED_MIN_N of the built sizes
+static bool packed_size(long long n) { return n >= GGP_PACKED_MIN_N && size_supported(n); }
+static int dispatch_row2(int N, const RowParams<float>& p, cudaStream_t st) {
+  switch (N) {
+#define X(n)                                                         \
+  case n:                                                            \
+    if constexpr (n >= GGP_PACKED_MIN_N) return launch_row2<n>(p, st); \
+    break;
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+static int dispatch_str2(int N, const StrParams<float>& p, long long nfast, long long nother, cudaStream_t st) {
+  switch (N) {
+#define X(n)                                                                        \
+  case n:                                                                           \
+    if constexpr (n >= GGP_PACKED_MIN_N) return launch_str2<n>(p, nfast, nother, st); \
+    break;
+    GGP_SIZES(X)
+#undef X
+  }
+  return (int)cudaErrorNotSupported;
+}
+#endif
 
 // ---- observables -------------------------------------------------------------------------------
 template <typename T>
@@ -212,6 +243,8 @@ struct PlanT : PlanBase {
   cpx<T>* V[4] = {nullptr, nullptr, nullptr, nullptr};
   cpx<T>* S[2] = {nullptr, nullptr};
   cpx<T>* tw[3] = {nullptr, nullptr, nullptr};
+  void* tw2[3] = {nullptr, nullptr, nullptr};  // duplicated twiddles of the packed two-line kernels (fp32 plans)
+  bool packed_ok = false;
   int dkind = 0;
   // separable scalar dispersion: exp_D = Dperp[all but the last axis] * Dline[last axis]
   bool sep = false;
@@ -411,7 +444,10 @@ struct PlanT : PlanBase {
       for (int a = 0; a < ndim; ++a) {
         const long long na = (slab && a == 2) ? n3g : n[a];
         for (int b = 0; b < a; ++b)
-          if (n[b] == na) tw[a] = tw[b];
+          if ((b == 2 && slab ? n3g : n[b]) == na) {
+            tw[a] = tw[b];
+            tw2[a] = tw2[b];
+          }
         if (tw[a]) continue;
         // per-pass coalesced layout, see fft_line.cuh
         std::vector<cpx<T>> h;
@@ -433,6 +469,31 @@ struct PlanT : PlanBase {
         }
         if ((rc = dalloc((void**)&tw[a], sizeof(cpx<T>) * h.size()))) return rc;
         GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(cpx<T>) * h.size(), cudaMemcpyHostToDevice));
+#ifdef GGP_PACKED
+        if constexpr (std::is_same<T, float>::value) {
+          // packed kernels: radix schedule of default_E<f2>, every entry duplicated into both lanes
+          if (M == 1 && packed_size(na) && !getenv("GGP_NO_PACKED")) {
+            std::vector<float> h2;
+            const long long N = na;
+            const long long E = default_E<f2>((int)N);
+            const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+            for (long long NS = 1; NS < N;) {
+              const long long R = (N / NS >= E) ? E : N / NS;
+              if (NS > 1)
+                for (long long r = 1; r < R; ++r)
+                  for (long long k = 0; k < NS; ++k) {
+                    const long double ang = -twopi * (long double)(r * k) / (long double)(NS * R);
+                    const float c = (float)cosl(ang), sn = (float)sinl(ang);
+                    h2.push_back(c); h2.push_back(c); h2.push_back(sn); h2.push_back(sn);
+                  }
+              NS *= R;
+            }
+            if (h2.empty()) h2.assign(4, 0.f);
+            if ((rc = dalloc(&tw2[a], sizeof(float) * h2.size()))) return rc;
+            GGP_CUDA(cudaMemcpy(tw2[a], h2.data(), sizeof(float) * h2.size(), cudaMemcpyHostToDevice));
+          }
+        }
+#endif
       }
     }
     memset(&pw, 0, sizeof(pw));
@@ -608,6 +669,18 @@ struct PlanT : PlanBase {
     p.flags = (pre ? 1 : 0) | (post ? 2 : 0);
     int rc = prof_begin(KC_ROW);
     if (rc) return rc;
+#ifdef GGP_PACKED
+    if constexpr (std::is_same<T, float>::value) {
+      // two rows per thread group with packed fp32x2 arithmetic (packed.cuh)
+      const bool any = hA.apply || hB.apply;
+      if (tw2[0] && M == 1 && (p.nlines % 2 == 0) && (!any || pw_variant() == PW_KERR)) {
+        p.tw2 = tw2[0];
+        GGP_LAUNCH(dispatch_row2((int)n[0], p, stream), "row2_kernel");
+        ++launches;
+        return prof_end();
+      }
+    }
+#endif
     GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pw_variant(), p, stream), "row_kernel");
     ++launches;
     return prof_end();
@@ -671,6 +744,17 @@ struct PlanT : PlanBase {
       ++launches;
       return prof_end();
     }
+#ifdef GGP_PACKED
+    if constexpr (std::is_same<T, float>::value) {
+      const bool dk_ok = mode != 1 || p.dkind == KIND_NONE || p.dkind == KIND_SCALAR || p.dkind == KIND_SEP;
+      if (tw2[ax] && M == 1 && g0 >= 4 && dk_ok) {
+        p.tw2 = tw2[ax];
+        GGP_LAUNCH(dispatch_str2(N, p, g0, nother, stream), "str2_kernel");
+        ++launches;
+        return prof_end();
+      }
+    }
+#endif
     GGP_LAUNCH(dispatch_str<T>(N, M, p, g0, nother, stream), "str_kernel");
     ++launches;
     return prof_end();

@@ -2,6 +2,9 @@
 // library builds in parallel.  Compiled with -DGGP_T=float|double -DGGP_N=<line length>.
 #include <cstdlib>
 #include "str_tma.cuh"
+#ifdef GGP_PACKED
+#include "packed.cuh"
+#endif
 
 namespace ggp {
 
@@ -137,6 +140,46 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st) {
   if (M == 2) return launch_oned_m<T, N, 2>(pwv, p, st);
   return (int)cudaErrorInvalidValue;
 }
+
+#if defined(GGP_PACKED) && GGP_N >= GGP_PACKED_MIN_N
+template <int N>
+int launch_row2(const RowParams<float>& p, cudaStream_t st) {
+  using K = KCfg<f2, N>;
+  const size_t smem = K::USES_SMEM ? (size_t)K::LPC * K::row_ls() * sizeof(cpx<f2>) : 0;
+  const long long pairs = p.nlines / 2;
+  const unsigned grid = (unsigned)((pairs + K::LPC - 1) / K::LPC);
+  auto k = row2_kernel<N>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  k<<<grid, K::ROW_THREADS, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+template <int N>
+int launch_str2(StrParams<float> p, long long nfast, long long nother, cudaStream_t st) {
+  using K = KCfg<f2, N>;
+  int W = K::WDEF;  // column pairs per CTA
+  if (const char* e = getenv("GGP_STR_W")) {
+    const int w = atoi(e) / 2;
+    if (w >= 1 && w <= K::WDEF && (w & (w - 1)) == 0) W = w;
+  }
+  while (2 * W > nfast) W >>= 1;
+  if (W < 1) return (int)cudaErrorInvalidConfiguration;
+  p.W = W;
+  p.logW = ilog2(W);
+  p.LS = K::str_ls(W);
+  p.ntx = nfast / (2 * W);
+  const size_t smem = K::USES_SMEM ? (size_t)W * p.LS * sizeof(cpx<f2>) : 0;
+  const long long grid = p.ntx * nother;
+  if (grid > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  auto k = str2_kernel<N>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  k<<<(unsigned)grid, W * K::TPL, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+template int launch_row2<GGP_N>(const RowParams<float>&, cudaStream_t);
+template int launch_str2<GGP_N>(StrParams<float>, long long, long long, cudaStream_t);
+#endif
 
 template int launch_row<GGP_T, GGP_N>(int, int, const RowParams<GGP_T>&, cudaStream_t);
 template int launch_str<GGP_T, GGP_N>(int, StrParams<GGP_T>, long long, long long, cudaStream_t);

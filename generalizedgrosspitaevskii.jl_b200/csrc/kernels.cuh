@@ -25,6 +25,7 @@ struct RowParams {
   PointwiseParams<T> pw;
   HalfStep<T> hs[2];  // trailing half-step of step n, leading half-step of step n+1
   int flags;          // bit 0: inverse FFT_x first, bit 1: forward FFT_x last
+  const void* tw2;    // twiddles of the packed two-line kernels (packed.cuh), fp32 plans only
 };
 
 template <typename T>
@@ -39,6 +40,7 @@ struct StrParams {
   int dkind;
   int mode;  // 0 forward only, 1 forward -> x D -> inverse, 2 inverse only
   int W, logW, LS;
+  const void* tw2;  // twiddles of the packed two-column kernel (packed.cuh), fp32 plans only
 };
 
 template <typename T>
@@ -130,6 +132,30 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
         half_step_point<T, M, PWV>(f, pw, hs[h], sidx0 + m * stride, gidx0 + m * stride, rnd[m]);
 #pragma unroll
         for (int c = 0; c < M; ++c) v[c][m] = f[c];
+      }
+    }
+  } else if constexpr (PWV == PW_KERR) {
+    // Real diagonal nonlinearity only: u_i <- cis(-dt G_i(|u|^2)) u_i is a pure phase, |u_j| is invariant under
+    // it, so the trailing half-step of step n and the leading half-step of step n+1 (same G, same |u|) are
+    // exactly ONE rotation by the summed angle -- half the sincos work of the fused kernel.
+    int napply = 0;
+    for (int h = 0; h < nh; ++h) napply += hs[h].apply ? 1 : 0;
+    if (napply) {
+      const T dts = pw.dt * (T)napply;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        T n2[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) n2[j] = cabs2(v[j][m]);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          T gre = pw.nl_c_re[i];
+#pragma unroll
+          for (int j = 0; j < M; ++j) gre += pw.nl_g_re[i][j] * n2[j];
+          T sn, cs;
+          sincos_t(-dts * gre, &sn, &cs);
+          v[i][m] = cmul(mk<T>(cs, sn), v[i][m]);
+        }
       }
     }
   } else {
