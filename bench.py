@@ -74,7 +74,7 @@ def make_workload(ns, name, nbatch=None, n=None, traj_range=None):
         N = n or 512
         rank, world = traj_range if traj_range is not None else (0, 1)
         pb = P.kerr3d_slab(ns, N=N, rank=rank, world=world, dtype=np.complex64)
-        return pb, dict(workload=f"C5: 3-D BEC Kerr GPE {N}^3 ComplexF32, slab-decomposed over {world} GPU(s) with an NCCL "
+        return pb, dict(workload=f"C5: 3-D BEC Kerr GPE {N}^3 ComplexF32, slab-decomposed over {world} GPU(s), all-to-all transposes fused into the FFT kernels as NVLink peer stores "
                                  "all-to-all transpose (BASELINE.json configs[4]; 1024^3 with --grid 1024)",
                         grid=[N, N, N], ncomp=1, nbatch=1, dtype="c64", points=N * N * N // world,
                         bytes_row=16, bytes_str=16, b_alg_contract=88)
@@ -536,6 +536,9 @@ def attach_comm(G, it, world, rank):
     raw = bytes(t.cpu().tolist())
     buf = C.create_string_buffer(raw, 128)
     G.lib.check(lib.ggp_comm_init(it.handle, world, rank, buf))
+    if it.slab is not None and not os.environ.get("GGP_SLAB_NCCL"):
+        # slab plans: peer-memory exchange fused into the FFT kernels (CUDA IPC handles gathered here)
+        G.parallel.attach_p2p(G, it, _DIST)
     if it.slab is None:
         it.observe(G.lib.OBS_NORM)      # warm-up collective: NCCL sets its channels up lazily on first use
 

@@ -19,7 +19,7 @@ OBS_DENSITY, OBS_MOMENTUM, OBS_NORM = 0, 1, 2
 EXPORTS = [
     "ggp_version", "ggp_device_count", "ggp_last_error", "ggp_plan_create", "ggp_plan_destroy",
     "ggp_set_state", "ggp_get_state", "ggp_step", "ggp_synchronize", "ggp_observe",
-    "ggp_comm_unique_id", "ggp_comm_init", "ggp_state_device_ptr", "ggp_timer_begin", "ggp_timer_end",
+    "ggp_comm_unique_id", "ggp_comm_init", "ggp_slab_ipc_export", "ggp_slab_ipc_attach", "ggp_state_device_ptr", "ggp_timer_begin", "ggp_timer_end",
     "ggp_launch_count", "ggp_host_alloc", "ggp_host_free", "ggp_device_bytes", "ggp_profile_enable",
     "ggp_profile_read", "ggp_debug_l2_flush", "ggp_debug_flush_only",
 ]
@@ -79,6 +79,8 @@ def load():
     lib.ggp_observe.argtypes = [vp, C.c_int, vp]
     lib.ggp_comm_unique_id.argtypes = [vp]
     lib.ggp_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ggp_slab_ipc_export.argtypes = [vp, vp]
+    lib.ggp_slab_ipc_attach.argtypes = [vp, vp]
     lib.ggp_state_device_ptr.argtypes = [vp, C.c_int]
     lib.ggp_state_device_ptr.restype = vp
     lib.ggp_timer_begin.argtypes = [vp]

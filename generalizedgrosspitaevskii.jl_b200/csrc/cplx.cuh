@@ -6,6 +6,14 @@
 
 namespace ggp {
 
+// Programmatic dependent launch (sm_90+): every kernel of the step chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, announces at its very start that the next kernel may
+// be scheduled (its CTAs take the SM slots this grid frees while it drains, with their parameters and index
+// arithmetic done), and blocks in pdl_wait() -- until the previous grid has completed and flushed -- right
+// before its first read of the field.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // f2: two fp32 values in one 64-bit register pair, operated on with Blackwell's packed fp32x2
 // instructions (add/sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2).  A cpx<f2> is TWO complex numbers
 // (lane 0 = line A, lane 1 = line B) that go through identical arithmetic: the FFT of two lines at
@@ -45,6 +53,45 @@ template <>
 __device__ __forceinline__ f2 cst<f2>(double c) {
   return mkf2((float)c, (float)c);
 }
+// low part of a constant: c - fl32(c).  The radix butterflies' internal twiddles (1/sqrt2, cos/sin of
+// multiples of pi/16) all round to fp32 values whose modulus is BELOW one (-0.7e-8 ... -2.9e-8), which
+// shrinks every transform by ~3e-8 and makes a ComplexF32 run lose norm at ~1e-7 per step -- the dominant,
+// systematic part of the fp32 error (tools/c64_error_probe.py).  Multiplying by (hi + lo) with one extra
+// FMA per product removes that bias.  fp64 does not need it.
+template <typename T>
+__device__ __forceinline__ T cst_lo(double c) {
+  return (T)0;
+}
+template <>
+__device__ __forceinline__ float cst_lo<float>(double c) {
+  return (float)(c - (double)(float)c);
+}
+template <>
+__device__ __forceinline__ f2 cst_lo<f2>(double c) {
+  const float l = (float)(c - (double)(float)c);
+  return mkf2(l, l);
+}
+template <typename T>
+struct Compensate {
+  static constexpr bool value = false;
+};
+#ifndef GGP_FAST_CONST
+template <>
+struct Compensate<float> {
+  static constexpr bool value = true;
+};
+template <>
+struct Compensate<f2> {
+  static constexpr bool value = true;
+};
+#endif
+// x * c for a compile-time constant c, bias-free in fp32
+template <typename T>
+__device__ __forceinline__ T mulc(T x, double c) {
+  if constexpr (Compensate<T>::value) return fma_(x, cst_lo<T>(c), x * cst<T>(c));
+  return x * cst<T>(c);
+}
+
 // scalar type behind T and number of lines it carries
 template <typename T>
 struct Lanes {
@@ -94,6 +141,36 @@ template <typename T>
 __device__ __forceinline__ T cabs2(cpx<T> a) {
   return fma_(a.y, a.y, a.x * a.x);
 }
+// Inter-pass twiddle factors and the factors of a separable exp_D.  Default: a plain complex number of the
+// plan's precision.  -DGGP_SPLIT_TWIDDLES (make SPLIT_TW=1): fp32 plans keep the double-precision value as
+// hi + lo (one 16-byte entry, one LDG.128) and multiply with four extra FMAs.  Measured (tools/
+// c64_error_probe.py, 256^2, 1000 steps): relative L2 distance to the fp64 run 5.0e-5 -> 4.1e-5 only -- the
+// fp32 error that grows linearly with the step count is the round-off of the butterflies themselves, which
+// repeats from step to step because the field changes slowly -- at the price of a 1.6x slower strided
+// kernel (doubled twiddle traffic through L1).  Hence off by default; profiles/r01_notes.md.
+template <typename T>
+struct TwT {
+  using type = cpx<T>;
+  static constexpr bool split = false;
+  static __device__ __forceinline__ cpx<T> mul(cpx<T> a, const type w) { return cmul(a, w); }
+  static __host__ type make(long double c, long double s) { return mk<T>((T)c, (T)s); }
+};
+#ifdef GGP_SPLIT_TWIDDLES
+template <>
+struct TwT<float> {
+  using type = float4;  // (hi.re, hi.im, lo.re, lo.im)
+  static constexpr bool split = true;
+  static __device__ __forceinline__ cpx<float> mul(cpx<float> a, const float4 w) {
+    return mk<float>(fmaf(a.x, w.x, fmaf(-a.y, w.y, fmaf(a.x, w.z, -a.y * w.w))),
+                     fmaf(a.x, w.y, fmaf(a.y, w.x, fmaf(a.x, w.w, a.y * w.z))));
+  }
+  static __host__ float4 make(long double c, long double s) {
+    const float ch = (float)c, sh = (float)s;
+    return make_float4(ch, sh, (float)(c - (long double)ch), (float)(s - (long double)sh));
+  }
+};
+#endif
+
 // multiply by  s*i  where s = DIR (DIR=-1: forward transform e^{-i..}, DIR=+1: inverse)
 template <typename T, int DIR>
 __device__ __forceinline__ cpx<T> mul_si(cpx<T> a) {
@@ -157,8 +234,7 @@ struct Dft {
           v[k + H] = mk<T>(ek.x + ok.y, ek.y - ok.x);
         }
       } else if (8 * k == R) {  // (1 + DIR*i)/sqrt2
-        const T h = cst<T>(0.70710678118654752440);
-        const T p = (ok.x + ok.y) * h, q = (ok.y - ok.x) * h;
+        const T p = mulc<T>(ok.x + ok.y, 0.70710678118654752440), q = mulc<T>(ok.y - ok.x, 0.70710678118654752440);
         if (DIR < 0) {  // t = (p, q)
           v[k] = mk<T>(ek.x + p, ek.y + q);
           v[k + H] = mk<T>(ek.x - p, ek.y - q);
@@ -167,8 +243,7 @@ struct Dft {
           v[k + H] = mk<T>(ek.x + q, ek.y - p);
         }
       } else if (8 * k == 3 * R) {  // (-1 + DIR*i)/sqrt2
-        const T h = cst<T>(0.70710678118654752440);
-        const T p = (ok.x + ok.y) * h, q = (ok.y - ok.x) * h;
+        const T p = mulc<T>(ok.x + ok.y, 0.70710678118654752440), q = mulc<T>(ok.y - ok.x, 0.70710678118654752440);
         if (DIR < 0) {  // t = (q, -p)
           v[k] = mk<T>(ek.x + q, ek.y - p);
           v[k + H] = mk<T>(ek.x - q, ek.y + p);
@@ -177,10 +252,16 @@ struct Dft {
           v[k + H] = mk<T>(ek.x + p, ek.y + q);
         }
       } else {
-        const T c = cst<T>(cos32(k * (32 / R)));
-        const T sn = cst<T>(DIR * sin32(k * (32 / R)));
-        const T msn = cst<T>(-DIR * sin32(k * (32 / R)));
-        const cpx<T> t = mk<T>(fma_(ok.y, msn, ok.x * c), fma_(ok.y, c, ok.x * sn));
+        const double cd = cos32(k * (32 / R)), sd = DIR * sin32(k * (32 / R));
+        const T c = cst<T>(cd), sn = cst<T>(sd), msn = cst<T>(-sd);
+        cpx<T> t;
+        if constexpr (Compensate<T>::value) {
+          const T cl = cst_lo<T>(cd), sl = cst_lo<T>(sd), msl = cst_lo<T>(-sd);
+          t = mk<T>(fma_(ok.x, c, fma_(ok.y, msn, fma_(ok.y, msl, ok.x * cl))),
+                    fma_(ok.y, c, fma_(ok.x, sn, fma_(ok.x, sl, ok.y * cl))));
+        } else {
+          t = mk<T>(fma_(ok.y, msn, ok.x * c), fma_(ok.y, c, ok.x * sn));
+        }
         v[k] = ek + t;
         v[k + H] = ek - t;
       }

@@ -24,8 +24,13 @@ struct IsPacked<f2> {
 };
 template <typename T>
 __host__ __device__ constexpr int default_E(int N) {
-  int e = (sizeof(T) == 4 || IsPacked<T>::value) ? 16 : 8;
-  while (N / e > 256) e *= 2;
+  // fp32 (and the packed pairs): radix 16, radix 32 only where a line would otherwise need more than 256
+  // threads; fp64: radix 8, radix 16 likewise -- never wider than 64 data registers per component
+  // (radix-32 fp64 = 128 data registers spills), so the longest fp64 lines take 512 threads instead.
+  const bool f32 = sizeof(T) == 4 || IsPacked<T>::value;
+  int e = f32 ? 16 : 8;
+  const int emax = f32 ? 32 : 16;
+  while (N / e > 256 && e < emax) e *= 2;
   return e < N ? e : N;
 }
 
@@ -70,7 +75,7 @@ struct Passes {
   static constexpr bool LASTP = (NS * R == N);
 
   static __device__ __forceinline__ void run(cpx<T> (&v)[E], const int t, cpx<T>* __restrict__ line,
-                                             const cpx<T>* __restrict__ tw) {
+                                             const typename TwT<T>::type* __restrict__ tw) {
     if constexpr (NS > 1) {
       if constexpr (TPL % E == 0) {
         // pad(t + m*TPL) = pad(t) + m*(TPL + TPL/E): one base, immediate offsets
@@ -91,12 +96,10 @@ struct Passes {
       const int b = t + q * TPL;
       const int k = b & (NS - 1);
       if constexpr (NS > 1) {
-        const cpx<T>* twk = tw + TWOFF + k;
+        static_assert(DIR < 0, "the inverse transform runs the forward code on conjugated data");
+        const typename TwT<T>::type* twk = tw + TWOFF + k;
 #pragma unroll
-        for (int r = 1; r < R; ++r) {
-          const cpx<T> w = twk[(r - 1) * NS];
-          a[r] = DIR < 0 ? cmul(a[r], w) : cmulc(a[r], w);
-        }
+        for (int r = 1; r < R; ++r) a[r] = TwT<T>::mul(a[r], twk[(r - 1) * NS]);
       }
       Dft<T, R, DIR>::run(a);
       if constexpr (LASTP) {
@@ -131,7 +134,7 @@ struct Passes {
 // transform of the same thread group, so synchronise before the first scatter.
 template <typename T, int N, int DIR, typename SYNC, bool PRESYNC>
 __device__ __forceinline__ void fft_line(cpx<T> (&v)[LineCfg<T, N>::E], const int t, cpx<T>* __restrict__ line,
-                                         const cpx<T>* __restrict__ tw) {
+                                         const typename TwT<T>::type* __restrict__ tw) {
   if (PRESYNC && LineCfg<T, N>::E < N) SYNC::sync();
   Passes<T, N, DIR, SYNC, 1>::run(v, t, line, tw);
 }

@@ -11,7 +11,10 @@
 
 #include "../../include/ggp.h"
 #include <type_traits>
+#include "kernels.cuh"
+#ifdef GGP_TMA
 #include "str_tma.cuh"
+#endif
 #ifdef GGP_PACKED
 #include "packed.cuh"
 #endif
@@ -78,6 +81,7 @@ static int dispatch_oned(int N, int M, int pwv, const OneDParams<T>& p, cudaStre
   }
   return (int)cudaErrorNotSupported;
 }
+#ifdef GGP_TMA
 template <typename T>
 static int dispatch_str_tma(int N, int M, const StrTmaParams<T>& p, long long nfast, long long nother, int sms,
                             cudaStream_t st) {
@@ -90,6 +94,7 @@ static int dispatch_str_tma(int N, int M, const StrTmaParams<T>& p, long long nf
   }
   return (int)cudaErrorNotSupported;
 }
+#endif
 template <typename T>
 static void dispatch_str_query(int N, long long nfast, int* W, int* LS, int* threads, int* us) {
   *W = 0;
@@ -168,6 +173,37 @@ __global__ void sum_kernel(const double* __restrict__ in, double* __restrict__ o
   if (threadIdx.x == 0) atomicAdd(out, sh[0]);
 }
 
+// Cross-GPU barrier of the slab decomposition (one CTA, lane q talks to rank q): publish this rank's epoch in
+// every peer's flag array (a release store at system scope; the peer stores of the preceding kernel are complete
+// at its end), then wait until every peer has published the same epoch in ours.  Bounded spin: a rank that died
+// must not hang the others -- after ~20 s the error word is set instead.
+struct SlabBarrierParams {
+  unsigned* peer_flags[GGP_MAX_PEERS];
+  unsigned* my_flags;
+  int* err;
+  int P, me;
+  unsigned epoch;
+};
+__global__ void slab_barrier_kernel(const SlabBarrierParams p) {
+  const int q = threadIdx.x;
+  if (q >= p.P || q == p.me) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[q] + p.me), "r"(p.epoch) : "memory");
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.my_flags + q) : "memory");
+    if ((int)(v - p.epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) {
+      *p.err = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
 // ---- plan ----------------------------------------------------------------------------------------
 enum { KC_ROW = 0, KC_STR_D = 1, KC_STR_FI = 2, KC_ONED = 3, KC_COUNT = 4 };
 
@@ -179,6 +215,8 @@ struct PlanBase {
   virtual int step(int64_t nsteps, const double* amp, const void* const* noise) = 0;
   virtual int observe(int kind, double* out) = 0;
   virtual void* state_ptr(int c) = 0;
+  virtual int ipc_export(void* blob) = 0;
+  virtual int ipc_attach(const void* blobs) = 0;
 
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -242,7 +280,7 @@ struct PlanT : PlanBase {
   cpx<T>* D[4] = {nullptr, nullptr, nullptr, nullptr};
   cpx<T>* V[4] = {nullptr, nullptr, nullptr, nullptr};
   cpx<T>* S[2] = {nullptr, nullptr};
-  cpx<T>* tw[3] = {nullptr, nullptr, nullptr};
+  typename TwT<T>::type* tw[3] = {nullptr, nullptr, nullptr};
   void* tw2[3] = {nullptr, nullptr, nullptr};  // duplicated twiddles of the packed two-line kernels (fp32 plans)
   bool packed_ok = false;
   int dkind = 0;
@@ -250,6 +288,7 @@ struct PlanT : PlanBase {
   bool sep = false;
   cpx<T>* Dperp = nullptr;
   cpx<T>* Dline = nullptr;
+  typename TwT<T>::type* Dsp[2] = {nullptr, nullptr};  // the same factors as hi + lo pairs (fp32 plans)
   PointwiseParams<T> pw;
   bool has_pointwise = false;
   int pump_kind = 0, noise_kind = 0, noise_real = 0;
@@ -268,17 +307,30 @@ struct PlanT : PlanBase {
   int P = 1, prank = 0;
   long long n2g = 1, n3g = 1, n2loc = 1, n3loc = 1;
   cpx<T>* xbuf[2] = {nullptr, nullptr};
-  cpx<T>* sendbuf[2] = {nullptr, nullptr};
+  cpx<T>* sendbuf[2] = {nullptr, nullptr};   // NCCL path only, allocated on first use
+  // fused transpose over peer memory (CUDA IPC): every rank maps every other rank's u, xbuf and barrier flags;
+  // the strided kernels then store their results directly into the owner's slab (StrParams::scatter)
+  bool p2p = false;
+  cpx<T>* peer_u[GGP_MAX_PEERS][2];
+  cpx<T>* peer_x[GGP_MAX_PEERS][2];
+  unsigned* peer_flags[GGP_MAX_PEERS];
+  unsigned* flags = nullptr;
+  int* bar_err = nullptr;
+  unsigned epoch = 0;
+  std::vector<void*> ipc_opened;
   // TMA path of the strided kernel, per strided axis (1, 2)
   bool tma_ok[3] = {false, false, false};
   bool tma_d[3] = {false, false, false};  // exp_D staged by TMA as well
+#ifdef GGP_TMA
   CUtensorMap tmap[3][2];
   CUtensorMap dmap[3][4];
+#endif
   int sm_count = 148;
 
   ~PlanT() override {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     for (void* p : allocs) cudaFree(p);
     if (flush_buf) cudaFree(flush_buf);
     if (ev0) cudaEventDestroy(ev0);
@@ -347,10 +399,11 @@ struct PlanT : PlanBase {
         dmax = std::max(dmax, std::abs(z));
         emax = std::max(emax, std::abs(z - perp[(size_t)q] * line[(size_t)l]));
       }
-    // Tolerance: a table computed in the plan's precision carries a rounding error of about eps*|phase|
-    // per entry, so the factorisation cannot reproduce it better than that.  fp64: 1e-13 (keeps the
-    // accumulated deviation far below the 1e-10 parity gate); fp32: 4e-6 (~32 eps; the same size as the
-    // table's own error for phases of a few tens of radians).  GGP_NO_SEP=1 disables the fast path.
+    // Tolerance.  fp64 plans: 1e-13 (keeps the accumulated deviation far below the 1e-10 parity gate).
+    // fp32 plans: 4e-6 (~32 eps).  A ComplexF32 problem has Float32 grids, so the reference's table is
+    // cis(-dt * fl32(D(k))) -- separable only up to eps32 * |phase| (C2: 1.2e-6 at the highest, unpopulated
+    // modes, 3e-10 at the populated ones); the factorised product stays inside the table's own rounding.
+    // GGP_NO_SEP=1 disables the fast path, GGP_SEP_TOL overrides the tolerance.
     double tol = (d.table_precision == GGP_C128 && sizeof(T) == 8) ? 1e-13 : 4e-6;
     if (const char* e = getenv("GGP_SEP_TOL")) tol = atof(e);
     if (!(emax <= tol * dmax)) return 0;
@@ -363,6 +416,16 @@ struct PlanT : PlanBase {
     if ((rc = dalloc((void**)&Dline, sizeof(cpx<T>) * (size_t)nl))) return rc;
     GGP_CUDA(cudaMemcpy(Dperp, hp.data(), sizeof(cpx<T>) * (size_t)np, cudaMemcpyHostToDevice));
     GGP_CUDA(cudaMemcpy(Dline, hl.data(), sizeof(cpx<T>) * (size_t)nl, cudaMemcpyHostToDevice));
+    if constexpr (TwT<T>::split) {
+      std::vector<typename TwT<T>::type> sp((size_t)np), sl((size_t)nl);
+      for (long long q = 0; q < np; ++q)
+        sp[(size_t)q] = TwT<T>::make((long double)perp[(size_t)q].real() * sc, (long double)perp[(size_t)q].imag() * sc);
+      for (long long l = 0; l < nl; ++l) sl[(size_t)l] = TwT<T>::make(line[(size_t)l].real(), line[(size_t)l].imag());
+      if ((rc = dalloc((void**)&Dsp[0], sizeof(sp[0]) * (size_t)np))) return rc;
+      if ((rc = dalloc((void**)&Dsp[1], sizeof(sl[0]) * (size_t)nl))) return rc;
+      GGP_CUDA(cudaMemcpy(Dsp[0], sp.data(), sizeof(sp[0]) * (size_t)np, cudaMemcpyHostToDevice));
+      GGP_CUDA(cudaMemcpy(Dsp[1], sl.data(), sizeof(sl[0]) * (size_t)nl, cudaMemcpyHostToDevice));
+    }
     sep = true;
     return 0;
   }
@@ -428,8 +491,11 @@ struct PlanT : PlanBase {
       for (int c = 0; c < M; ++c) {
         int rc2;
         if ((rc2 = dalloc((void**)&xbuf[c], bytes))) return rc2;
-        if ((rc2 = dalloc((void**)&sendbuf[c], bytes))) return rc2;
       }
+      int rc3;
+      if ((rc3 = dalloc((void**)&flags, 256))) return rc3;
+      GGP_CUDA(cudaMemsetAsync(flags, 0, 256, stream));
+      bar_err = (int*)(flags + GGP_MAX_PEERS);
     }
     // tables.  The inverse transform is unnormalised on the device; the reference's 1/prod(n)
     // (ScaledPlan, src/misc.jl:56) is folded into exp_D -- exact for power-of-two sizes.
@@ -450,7 +516,7 @@ struct PlanT : PlanBase {
           }
         if (tw[a]) continue;
         // per-pass coalesced layout, see fft_line.cuh
-        std::vector<cpx<T>> h;
+        std::vector<typename TwT<T>::type> h;
         {
           const long long N = na;
           const long long E = default_E<T>((int)N);
@@ -461,14 +527,14 @@ struct PlanT : PlanBase {
               for (long long r = 1; r < R; ++r)
                 for (long long k = 0; k < NS; ++k) {
                   const long double ang = -twopi * (long double)(r * k) / (long double)(NS * R);
-                  h.push_back(mk<T>((T)cosl(ang), (T)sinl(ang)));
+                  h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
                 }
             NS *= R;
           }
-          if (h.empty()) h.push_back(mk<T>((T)1, (T)0));
+          if (h.empty()) h.push_back(TwT<T>::make(1.0L, 0.0L));
         }
-        if ((rc = dalloc((void**)&tw[a], sizeof(cpx<T>) * h.size()))) return rc;
-        GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(cpx<T>) * h.size(), cudaMemcpyHostToDevice));
+        if ((rc = dalloc((void**)&tw[a], sizeof(h[0]) * h.size()))) return rc;
+        GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice));
 #ifdef GGP_PACKED
         if constexpr (std::is_same<T, float>::value) {
           // packed kernels: radix schedule of default_E<f2>, every entry duplicated into both lanes
@@ -553,6 +619,7 @@ struct PlanT : PlanBase {
     cudaDeviceProp prop;
     GGP_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
+#ifdef GGP_TMA
     // The TMA-fed persistent variant is opt-in (GGP_TMA=1): with 32-byte box rows (W = 4 complex64) it
     // measured slower than the LDG variant at two CTAs per SM on C2 (profiles/r01_notes.md).
     if (!getenv("GGP_TMA") || getenv("GGP_NO_TMA") || slab) return 0;
@@ -610,6 +677,7 @@ struct PlanT : PlanBase {
         }
       }
     }
+#endif
     return 0;
   }
 
@@ -623,6 +691,7 @@ struct PlanT : PlanBase {
     const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
     for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(uh[c], u[c], bytes, cudaMemcpyDeviceToHost, stream));
     GGP_CUDA(cudaStreamSynchronize(stream));
+    if (p2p) return barrier_status();
     return 0;
   }
   void* state_ptr(int c) override { return (c >= 0 && c < M) ? (void*)u[c] : nullptr; }
@@ -687,7 +756,9 @@ struct PlanT : PlanBase {
   }
 
   // strided pass along axis `ax` (1 or 2).  yslab: operate on xbuf in the transposed (n1, n2loc, n3g) layout.
-  int run_str(int ax, int mode, bool yslab = false) {
+  // scatter: 0 in place; 1 = y pass of the z-slab, results into the y-slabs (xbuf) of their owners; 2 = z pass of
+  // the y-slab, results into the z-slabs (u) of their owners (fused all-to-all transpose over peer memory).
+  int run_str(int ax, int mode, bool yslab = false, int scatter = 0) {
     StrParams<T> p;
     memset(&p, 0, sizeof(p));
     const long long g0 = n[0], g1 = yslab ? n2loc : n[1], g2 = yslab ? n3g : n[2];
@@ -699,6 +770,8 @@ struct PlanT : PlanBase {
     if (sep && mode == 1) {
       p.D[0] = Dperp;
       p.D[1] = Dline;
+      p.Dsp[0] = Dsp[0];
+      p.Dsp[1] = Dsp[1];
       p.dkind = KIND_SEP;
     }
     p.mode = mode;
@@ -719,8 +792,26 @@ struct PlanT : PlanBase {
       nother = g1 * nbatch;
     }
     const int N = (int)(ax == 1 ? g1 : g2);
+    if (scatter) {
+      p.scatter = scatter;
+      for (int q = 0; q < P; ++q)
+        for (int c = 0; c < M; ++c) p.dst[q][c] = scatter == 1 ? peer_x[q][c] : peer_u[q][c];
+      if (scatter == 1) {          // (x, j, zl) of u  ->  rank j / n2loc, (x, j % n2loc, prank*n3loc + zl) of its xbuf
+        p.dst_shift = ilog2((int)n2loc);
+        p.dst_ls = n[0];
+        p.dst_s1 = n[0] * n2loc;
+        p.dst_base = n[0] * n2loc * (long long)prank * n3loc;
+      } else {                     // (x, yl, j) of xbuf  ->  rank j / n3loc, (x, prank*n2loc + yl, j % n3loc) of its u
+        p.dst_shift = ilog2((int)n3loc);
+        p.dst_ls = n[0] * n2g;
+        p.dst_s1 = n[0];
+        p.dst_base = n[0] * (long long)prank * n2loc;
+      }
+      p.dst_s2 = 0;
+    }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
+#ifdef GGP_TMA
     if (tma_ok[ax] && !slab) {
       StrTmaParams<T> q;
       memset(&q, 0, sizeof(q));
@@ -744,6 +835,7 @@ struct PlanT : PlanBase {
       ++launches;
       return prof_end();
     }
+#endif
 #ifdef GGP_PACKED
     if constexpr (std::is_same<T, float>::value) {
       const bool dk_ok = mode != 1 || p.dkind == KIND_NONE || p.dkind == KIND_SCALAR || p.dkind == KIND_SEP;
@@ -764,8 +856,13 @@ struct PlanT : PlanBase {
   // forward: z-slabs u (n1, n2g, n3loc) -> y-slabs xbuf (n1, n2loc, n3g);  backward: the inverse.
   int transpose(bool forward) {
 #ifdef GGP_WITH_NCCL
-    if (!comm) return fail(GGP_ERR_NCCL, "slab plan without communicator: call ggp_comm_init first");
+    if (!comm) return fail(GGP_ERR_NCCL, "slab plan without communicator: call ggp_comm_init or ggp_slab_ipc_attach first");
     const size_t esz = sizeof(cpx<T>);
+    for (int c = 0; c < M; ++c)
+      if (!sendbuf[c]) {
+        int rc2 = dalloc((void**)&sendbuf[c], esz * (size_t)nspatial);
+        if (rc2) return rc2;
+      }
     const long long blk = n[0] * n2loc * n3loc;                  // elements exchanged with each peer
     const size_t width = (size_t)(n[0] * n2loc) * esz;           // one (x, y-range) chunk
     const size_t zpitch = (size_t)(n[0] * n2g) * esz;            // one z-plane of the z-slab
@@ -810,6 +907,76 @@ struct PlanT : PlanBase {
     (void)forward;
     return fail(GGP_ERR_NCCL, "libggp was built without NCCL");
 #endif
+  }
+
+  int slab_barrier() {
+    SlabBarrierParams b;
+    memset(&b, 0, sizeof(b));
+    for (int q = 0; q < P; ++q) b.peer_flags[q] = peer_flags[q];
+    b.my_flags = flags;
+    b.err = bar_err;
+    b.P = P;
+    b.me = prank;
+    b.epoch = ++epoch;
+    slab_barrier_kernel<<<1, 32, 0, stream>>>(b);
+    GGP_CUDA(cudaGetLastError());
+    ++launches;
+    return 0;
+  }
+
+  // CUDA IPC handles of this rank's u, xbuf and flags (see ggp_slab_ipc_export)
+  int ipc_export(void* blob) override {
+    if (!slab) return fail(GGP_ERR_INVALID, "ggp_slab_ipc_export: not a slab plan");
+    unsigned char* o = (unsigned char*)blob;
+    memset(o, 0, GGP_IPC_BLOB_BYTES);
+    int32_t hdr[4] = {0x47475031, M, P, prank};
+    memcpy(o, hdr, sizeof(hdr));
+    cudaIpcMemHandle_t h;
+    size_t off = 64;
+    void* ptrs[5] = {u[0], M > 1 ? u[1] : nullptr, xbuf[0], M > 1 ? xbuf[1] : nullptr, flags};
+    for (int i = 0; i < 5; ++i, off += sizeof(h)) {
+      if (!ptrs[i]) continue;
+      GGP_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+      memcpy(o + off, &h, sizeof(h));
+    }
+    return 0;
+  }
+  int ipc_attach(const void* blobs) override {
+    if (!slab) return fail(GGP_ERR_INVALID, "ggp_slab_ipc_attach: not a slab plan");
+    if (P > GGP_MAX_PEERS) return fail(GGP_ERR_UNSUPPORTED, "peer exchange supports at most 8 ranks");
+    const unsigned char* b = (const unsigned char*)blobs;
+    for (int q = 0; q < P; ++q) {
+      const unsigned char* o = b + (size_t)q * GGP_IPC_BLOB_BYTES;
+      int32_t hdr[4];
+      memcpy(hdr, o, sizeof(hdr));
+      if (hdr[0] != 0x47475031 || hdr[1] != M || hdr[2] != P || hdr[3] != q)
+        return fail(GGP_ERR_INVALID, "ggp_slab_ipc_attach: blob " + std::to_string(q) + " does not belong to rank " + std::to_string(q));
+      void* ptrs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (q == prank) {
+        ptrs[0] = u[0]; ptrs[1] = u[1]; ptrs[2] = xbuf[0]; ptrs[3] = xbuf[1]; ptrs[4] = flags;
+      } else {
+        size_t off = 64;
+        for (int i = 0; i < 5; ++i, off += sizeof(cudaIpcMemHandle_t)) {
+          if ((i == 1 || i == 3) && M < 2) continue;
+          cudaIpcMemHandle_t h;
+          memcpy(&h, o + off, sizeof(h));
+          cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess);
+          if (e != cudaSuccess)
+            return fail(GGP_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(q) + "): " + cudaGetErrorString(e));
+          ipc_opened.push_back(ptrs[i]);
+        }
+      }
+      peer_u[q][0] = (cpx<T>*)ptrs[0]; peer_u[q][1] = (cpx<T>*)ptrs[1];
+      peer_x[q][0] = (cpx<T>*)ptrs[2]; peer_x[q][1] = (cpx<T>*)ptrs[3];
+      peer_flags[q] = (unsigned*)ptrs[4];
+    }
+    p2p = getenv("GGP_SLAB_NCCL") == nullptr;
+    return 0;
+  }
+  int barrier_status() {
+    int e = 0;
+    if (bar_err) GGP_CUDA(cudaMemcpy(&e, bar_err, sizeof(int), cudaMemcpyDeviceToHost));
+    return e ? fail(GGP_ERR_NCCL, "slab barrier timed out: a peer rank did not arrive") : 0;
   }
 
   // which compile-time variant of the half-step covers this problem (pointwise.cuh)
@@ -897,6 +1064,12 @@ struct PlanT : PlanBase {
       } else if (!slab) {
         if ((rc = run_str(1, 0))) return rc;
         if ((rc = run_str(2, 1))) return rc;
+        if ((rc = run_str(1, 2))) return rc;
+      } else if (p2p) {
+        if ((rc = run_str(1, 0, false, 1))) return rc;
+        if ((rc = slab_barrier())) return rc;
+        if ((rc = run_str(2, 1, true, 2))) return rc;
+        if ((rc = slab_barrier())) return rc;
         if ((rc = run_str(1, 2))) return rc;
       } else {
         if ((rc = run_str(1, 0))) return rc;
@@ -1090,6 +1263,17 @@ int ggp_comm_init(ggp_plan* p, int nranks, int rank, const void* id) {
   (void)nranks; (void)rank; (void)id;
   return fail(GGP_ERR_NCCL, "libggp was built without NCCL");
 #endif
+}
+
+int ggp_slab_ipc_export(ggp_plan* p, void* blob) {
+  GGP_ENTER(p);
+  if (!blob) return fail(GGP_ERR_INVALID, "blob is NULL");
+  return p->impl->ipc_export(blob);
+}
+int ggp_slab_ipc_attach(ggp_plan* p, const void* blobs) {
+  GGP_ENTER(p);
+  if (!blobs) return fail(GGP_ERR_INVALID, "blobs is NULL");
+  return p->impl->ipc_attach(blobs);
 }
 
 void* ggp_state_device_ptr(ggp_plan* p, int c) { return (p && p->impl) ? p->impl->state_ptr(c) : nullptr; }

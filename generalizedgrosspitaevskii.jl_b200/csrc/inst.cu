@@ -1,7 +1,11 @@
 // One translation unit per (GGP_T, GGP_N): explicit instantiation of the launchers, so the
 // library builds in parallel.  Compiled with -DGGP_T=float|double -DGGP_N=<line length>.
 #include <cstdlib>
+#include <cstring>
+#include "kernels.cuh"
+#ifdef GGP_TMA
 #include "str_tma.cuh"
+#endif
 #ifdef GGP_PACKED
 #include "packed.cuh"
 #endif
@@ -17,6 +21,29 @@ static int set_smem(KernelT k, size_t bytes) {
   return 0;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait() in cplx.cuh) when the grid is at least about
+// one full wave of the GPU: the next kernel's CTAs then slip into the SM slots this grid frees while it
+// drains (measured on C2 chained: 63.7 -> 61.8 us/step; 4096^2: 313.9 -> 308.2).  For grids below one wave it is
+// counter-productive (1024^2: 24.7 -> 29.8 us/step: the early CTAs land wherever a slot frees first and
+// unbalance the SMs), so those launch the plain way.  GGP_NO_PDL=1 / GGP_PDL=1 force it off / on.
+template <typename P>
+static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const P& p) {
+  static const int mode = getenv("GGP_NO_PDL") ? 0 : (getenv("GGP_PDL") ? 2 : 1);
+  const bool pdl = mode == 2 || (mode == 1 && (unsigned long long)grid * block >= 148ull * 1024ull);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, k, p);
+}
+
 template <typename T, int N, int M, int PWV>
 static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   using K = KCfg<T, N>;
@@ -25,8 +52,7 @@ static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   auto k = row_kernel<T, N, M, PWV>;
   int e = set_smem(k, smem);
   if (e) return e;
-  k<<<grid, K::ROW_THREADS, smem, st>>>(p);
-  return (int)cudaGetLastError();
+  return launch_pdl<RowParams<T>>(k, grid, K::ROW_THREADS, smem, st, p);
 }
 
 template <typename T, int N, int M>
@@ -58,6 +84,7 @@ void str_query(long long nfast, int* W_, int* LS_, int* threads, int* uses_smem)
   *uses_smem = K::USES_SMEM ? 1 : 0;
 }
 
+#ifdef GGP_TMA
 template <typename T, int N, int M>
 static int launch_str_tma_m(StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
   using K = KCfg<T, N>;
@@ -89,6 +116,8 @@ int launch_str_tma(int M, StrTmaParams<T> p, long long nfast, long long nother, 
   return (int)cudaErrorInvalidValue;
 }
 
+#endif
+
 template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
@@ -104,8 +133,7 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   auto k = str_kernel<T, N, M>;
   int e = set_smem(k, smem);
   if (e) return e;
-  k<<<(unsigned)grid, W * K::TPL, smem, st>>>(p);
-  return (int)cudaGetLastError();
+  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p);
 }
 
 template <typename T, int N>
@@ -123,8 +151,7 @@ static int launch_oned_mp(const OneDParams<T>& p, cudaStream_t st) {
   auto k = oned_kernel<T, N, M, PWV>;
   int e = set_smem(k, smem);
   if (e) return e;
-  k<<<grid, K::ROW_THREADS, smem, st>>>(p);
-  return (int)cudaGetLastError();
+  return launch_pdl<OneDParams<T>>(k, grid, K::ROW_THREADS, smem, st, p);
 }
 
 template <typename T, int N, int M>
@@ -184,7 +211,9 @@ template int launch_str2<GGP_N>(StrParams<float>, long long, long long, cudaStre
 template int launch_row<GGP_T, GGP_N>(int, int, const RowParams<GGP_T>&, cudaStream_t);
 template int launch_str<GGP_T, GGP_N>(int, StrParams<GGP_T>, long long, long long, cudaStream_t);
 template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaStream_t);
+#ifdef GGP_TMA
 template int launch_str_tma<GGP_T, GGP_N>(int, StrTmaParams<GGP_T>, long long, long long, int, cudaStream_t);
+#endif
 template void str_query<GGP_T, GGP_N>(long long, int*, int*, int*, int*);
 
 }  // namespace ggp

@@ -14,12 +14,14 @@
 #include "fft_line.cuh"
 #include "pointwise.cuh"
 
+#define GGP_MAX_PEERS 8
+
 namespace ggp {
 
 template <typename T>
 struct RowParams {
   cpx<T>* u[2];
-  const cpx<T>* tw;
+  const typename TwT<T>::type* tw;
   long long nlines;           // (nspatial / N) * nbatch
   long long lines_per_image;  // nspatial / N ; spatial table line = line % lines_per_image
   PointwiseParams<T> pw;
@@ -31,22 +33,30 @@ struct RowParams {
 template <typename T>
 struct StrParams {
   cpx<T>* u[2];
-  const cpx<T>* tw;
+  const typename TwT<T>::type* tw;
   long long ls;      // stride (elements) between consecutive points of a line
   long long ntx;     // tiles of W along the fast axis
   long long no1, s1, s2;  // remaining dims: offset = (o % no1) * s1 + (o / no1) * s2
   long long ts1;     // table stride of remaining dim 1 (tables do not have the batch dim)
   const cpx<T>* D[4];
+  const typename TwT<T>::type* Dsp[2];  // KIND_SEP factors (D_perp, D_line) as hi + lo pairs (fp32 plans)
   int dkind;
   int mode;  // 0 forward only, 1 forward -> x D -> inverse, 2 inverse only
   int W, logW, LS;
   const void* tw2;  // twiddles of the packed two-column kernel (packed.cuh), fp32 plans only
+  // Slab decomposition, fused transpose: when scatter != 0 the transformed line is not written back in place
+  // but straight into the slabs of the ranks that own it after the all-to-all transpose -- peer memory mapped
+  // with CUDA IPC, plain stores over NVLink (own rank: local HBM).  Line point j goes to rank j >> dst_shift,
+  // element  dst_base + x + o1*dst_s1 + o2*dst_s2 + (j & mask)*dst_ls  of dst[rank][component].
+  cpx<T>* dst[GGP_MAX_PEERS][2];
+  long long dst_ls, dst_s1, dst_s2, dst_base;
+  int scatter, dst_shift;
 };
 
 template <typename T>
 struct OneDParams {
   cpx<T>* u[2];
-  const cpx<T>* tw;
+  const typename TwT<T>::type* tw;
   long long nlines;
   PointwiseParams<T> pw;
   const HalfStep<T>* hs;  // 2 * nsteps entries (device)
@@ -76,10 +86,24 @@ struct KCfg {
     return ls;
   }
   static constexpr bool USES_SMEM = E < N;
-  // strided kernel: W adjacent fast-axis positions per CTA (coalescing width)
+  // strided kernel: W adjacent fast-axis positions per CTA (coalescing width): one 32-byte sector per row
+  // (4 complex64 / 2 complex128), halved for the long lines so that a CTA never exceeds 512 threads -- a
+  // 1024-thread CTA fills the register file alone and runs its load / transform / store phases in
+  // lock-step with nothing to overlap them (4096^2 c64: 219 us per pass before, profiles/r01_notes.md).
   static constexpr int WMIN = sizeof(T) == 4 ? 4 : 2;
-  static constexpr int WDEF = (256 / TPL) < WMIN ? WMIN : ((256 / TPL) > 32 ? 32 : (256 / TPL));
+  static constexpr int WCAP = (512 / TPL) < 1 ? 1 : (512 / TPL);
+  static constexpr int WWANT = (256 / TPL) < WMIN ? WMIN : ((256 / TPL) > 32 ? 32 : (256 / TPL));
+  static constexpr int WDEF = WWANT < WCAP ? WWANT : WCAP;
   static constexpr int STR_THREADS = WDEF * TPL;
+  // registers: with at most 32 words of field data per thread the kernels fit 64 registers, and the launch
+  // bounds ask for as many CTAs per SM as that allows; wider data (M = 2, long fp64 lines) takes what it needs
+  __host__ __device__ static constexpr int data_regs(int M) { return M * E * (int)sizeof(cpx<T>) / 4; }
+  __host__ __device__ static constexpr int str_min_blocks(int M) {
+    return data_regs(M) <= 32 ? 1024 / STR_THREADS : 1;
+  }
+  __host__ __device__ static constexpr int row_min_blocks(int M, int pwv) {
+    return (data_regs(M) <= 32 && pwv != PW_STOCH) ? 1024 / ROW_THREADS : 1;
+  }
   using RowSync = typename std::conditional<(TPL <= 32), SyncWarp, SyncBlock>::type;
 };
 
@@ -95,7 +119,7 @@ __device__ __forceinline__ void conj_all(cpx<T> (&v)[E]) {
 // instruction-cache misses (ncu: stall_no_instructions dominant, profiles/r01_notes.md).
 template <typename T, int N, int M, typename SYNC>
 __device__ __forceinline__ void fft_fwd_all(cpx<T> (&v)[M][LineCfg<T, N>::E], const int t, cpx<T>* sl, const int LS,
-                                            const cpx<T>* __restrict__ tw, const bool inverse) {
+                                            const typename TwT<T>::type* __restrict__ tw, const bool inverse) {
 #pragma unroll
   for (int c = 0; c < M; ++c) {
     if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
@@ -152,9 +176,9 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
           T gre = pw.nl_c_re[i];
 #pragma unroll
           for (int j = 0; j < M; ++j) gre += pw.nl_g_re[i][j] * n2[j];
-          T sn, cs;
-          sincos_t(-dts * gre, &sn, &cs);
-          v[i][m] = cmul(mk<T>(cs, sn), v[i][m]);
+          T sn, cm1;
+          sincosm1_t(-dts * gre, &sn, &cm1);
+          v[i][m] = rotate_m1(v[i][m], cm1, sn);
         }
       }
     }
@@ -177,7 +201,7 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
 
 // flags: bit 0 = PRE (inverse FFT_x before the half-steps), bit 1 = POST (forward FFT_x after)
 template <typename T, int N, int M, int PWV>
-__global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowParams<T> p) {
+__global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_blocks(M, PWV)) row_kernel(const RowParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL, LPC = K::LPC, LS = K::row_ls();
   using SYNC = typename K::RowSync;
@@ -191,6 +215,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowP
   const long long soff = (line % p.lines_per_image) * N + t;
   cpx<T>* sl = smem + (size_t)grp * M * LS;
 
+  pdl_launch_dependents();
+  pdl_wait();
   cpx<T> v[M][E];
 #pragma unroll
   for (int c = 0; c < M; ++c)
@@ -212,7 +238,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) row_kernel(const RowP
 
 // mode 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
 template <typename T, int N, int M>
-__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>::STR_THREADS <= 512) ? 1024 / KCfg<T, N>::STR_THREADS : 1)
+__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_blocks(M))
     str_kernel(const StrParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
@@ -228,6 +254,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
   const long long mstride = (long long)TPL * p.ls;
   cpx<T>* sl = smem + (size_t)xw * M * p.LS;
 
+  pdl_launch_dependents();
+  pdl_wait();
   cpx<T> v[M][E];
 #pragma unroll
   for (int c = 0; c < M; ++c)
@@ -240,13 +268,27 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
     fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
     if (it == 0 && p.mode == 1) {
       if (p.dkind == KIND_SEP) {
-        const cpx<T> dperp = p.D[0][toff - (long long)t * p.ls];
-        const cpx<T>* dline = p.D[1] + t;
+        if constexpr (TwT<T>::split) {
+          // fp32: both factors carry their rounding residual (hi + lo) and are applied one after the other
+          // with compensated products -- a table rounded to fp32 is a fixed per-mode error that adds up
+          // linearly over the steps of a run (see TwT in cplx.cuh)
+          const typename TwT<T>::type dperp = p.Dsp[0][toff - (long long)t * p.ls];
+          const typename TwT<T>::type* dline = p.Dsp[1] + t;
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-          const cpx<T> d = cmul(dperp, dline[m * TPL]);
+          for (int m = 0; m < E; ++m) {
+            const typename TwT<T>::type dl = dline[m * TPL];
 #pragma unroll
-          for (int c = 0; c < M; ++c) v[c][m] = cmul(d, v[c][m]);
+            for (int c = 0; c < M; ++c) v[c][m] = TwT<T>::mul(TwT<T>::mul(v[c][m], dl), dperp);
+          }
+        } else {
+          const cpx<T> dperp = p.D[0][toff - (long long)t * p.ls];
+          const cpx<T>* dline = p.D[1] + t;
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const cpx<T> d = cmul(dperp, dline[m * TPL]);
+#pragma unroll
+            for (int c = 0; c < M; ++c) v[c][m] = cmul(d, v[c][m]);
+          }
         }
       } else {
 #pragma unroll
@@ -260,6 +302,18 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>
         }
       }
     }
+  }
+  if (p.scatter) {
+    const long long dbase = p.dst_base + xt * p.W + xw + o1 * p.dst_s1 + o2 * p.dst_s2;
+    const int mask = (1 << p.dst_shift) - 1;
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int j = t + m * TPL;
+        p.dst[j >> p.dst_shift][c][dbase + (long long)(j & mask) * p.dst_ls] = v[c][m];
+      }
+    return;
   }
 #pragma unroll
   for (int c = 0; c < M; ++c)
@@ -281,6 +335,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS) oned_kernel(const One
   const long long goff = line * N + t;
   cpx<T>* sl = smem + (size_t)grp * M * LS;
 
+  pdl_launch_dependents();
+  pdl_wait();
   cpx<T> v[M][E];
 #pragma unroll
   for (int c = 0; c < M; ++c)

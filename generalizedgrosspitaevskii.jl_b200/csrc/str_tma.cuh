@@ -20,7 +20,7 @@ struct alignas(64) StrTmaParams {
   int stage_d;          // 1: the exp_D tile is staged through shared memory by TMA as well
   int nplanes;          // planes of exp_D (1, M or M*M)
   cpx<T>* u[2];
-  const cpx<T>* tw;
+  const typename TwT<T>::type* tw;
   long long ls;        // stride (elements) between consecutive points of a line
   long long ntx;       // tiles of W along the fast axis
   long long ntiles;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename T, int N, int M>
-__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, (M == 1 && KCfg<T, N>::STR_THREADS <= 512) ? 1024 / KCfg<T, N>::STR_THREADS : 1)
+__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_blocks(M))
     str_tma_kernel(const __grid_constant__ StrTmaParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;

@@ -51,6 +51,23 @@ def attach_nccl(G, it, dist, device="cuda"):
     G.lib.check(lib.ggp_comm_init(it.handle, dist.get_world_size(), dist.get_rank(), buf))
 
 
+IPC_BLOB_BYTES = 512
+
+
+def attach_p2p(G, it, dist):
+    """Slab-decomposed plans: map every rank's slabs into every other rank (CUDA IPC handles gathered with
+    torch.distributed -- plumbing only) so that the strided FFT kernels write across NVLink directly
+    (ggp_slab_ipc_export / ggp_slab_ipc_attach, include/ggp.h)."""
+    lib = G.lib.load()
+    blob = C.create_string_buffer(IPC_BLOB_BYTES)
+    G.lib.check(lib.ggp_slab_ipc_export(it.handle, blob))
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, bytes(blob.raw))
+    allb = C.create_string_buffer(b"".join(gathered), IPC_BLOB_BYTES * dist.get_world_size())
+    G.lib.check(lib.ggp_slab_ipc_attach(it.handle, allb))
+    dist.barrier()
+
+
 def allreduce_observable(local: np.ndarray, dist) -> np.ndarray:
     """Host-side sum over ranks of an observable that was computed per rank (used when the plan has
     no NCCL communicator attached, e.g. the gloo tests)."""

@@ -173,6 +173,17 @@ int ggp_observe(ggp_plan *plan, int kind, double *out_host);
 int ggp_comm_unique_id(void *unique_id_128);
 int ggp_comm_init(ggp_plan *plan, int nranks, int rank, const void *unique_id_128);
 
+/* Slab decomposition without NCCL on the data path: the all-to-all transposes are fused into the strided FFT
+   kernels, which store their results straight into the slabs of the ranks that own them afterwards (peer
+   memory over NVLink, mapped with CUDA IPC) -- no pack, send/receive or unpack sweeps.  Every rank exports a
+   blob of GGP_IPC_BLOB_BYTES, the caller gathers them (rank order, its own plumbing) and hands the
+   concatenation to every rank; a host-side barrier must follow before the first ggp_step.  Replaces the
+   ncclSend/ncclRecv transposes that a plan uses when only ggp_comm_init was called (GGP_SLAB_NCCL=1 keeps
+   those).  New in this library: the reference has no multi-GPU path. */
+#define GGP_IPC_BLOB_BYTES 512
+int ggp_slab_ipc_export(ggp_plan *plan, void *blob);
+int ggp_slab_ipc_attach(ggp_plan *plan, const void *blobs_in_rank_order);
+
 /* Harness helpers (bench / tests): device pointers, device-side timing on the plan's stream,
    pinned host memory, and the number of kernels launched so far. */
 void *ggp_state_device_ptr(ggp_plan *plan, int comp);

@@ -1,5 +1,6 @@
-"""3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2 GPUs, NCCL all-to-all transpose for
-the z pass, compared with the unsharded CPU oracle.  Needs >= 2 CUDA devices (gpurun --gpus 2)."""
+"""3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2 GPUs, compared with the unsharded CPU
+oracle -- once with the transposes fused into the FFT kernels as peer stores over NVLink (CUDA IPC, the
+default), once with the ncclSend/ncclRecv transposes.  Needs >= 2 CUDA devices (gpurun --gpus 2)."""
 import os
 import sys
 
@@ -43,7 +44,7 @@ def _cases(ns):
     return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, p2p):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -60,6 +61,8 @@ def _worker(rank, world, port, q):
         it = G.init(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"], device=rank,
                     slab=(rank, world))
         G.parallel.attach_nccl(G, it, dist)
+        if p2p:
+            G.parallel.attach_p2p(G, it, dist)
         ts, sol = G.solve_(it)
         it.close()
         gathered = [None] * world
@@ -72,15 +75,16 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_slab_decomposition_matches_oracle():
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer_stores", "nccl"])
+def test_slab_decomposition_matches_oracle(p2p):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ggp_oracle as O
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29600 + (os.getpid() % 300) + (301 if p2p else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     results = q.get(timeout=600)
