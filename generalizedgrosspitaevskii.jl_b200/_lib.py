@@ -7,6 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggp.so")
+LIB_PATH = os.environ.get("GGP_LIBRARY", LIB_PATH)  # A/B measurements of kernel variants (tools/)
 
 GGP_ABI_VERSION = 2
 GGP_C64, GGP_C128 = 0, 1

@@ -11,8 +11,13 @@ namespace ggp {
 // be scheduled (its CTAs take the SM slots this grid frees while it drains, with their parameters and index
 // arithmetic done), and blocks in pdl_wait() -- until the previous grid has completed and flushed -- right
 // before its first read of the field.  Without the launch attribute both are no-ops.
+#ifdef GGP_NO_PDL_ASM
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // f2: two fp32 values in one 64-bit register pair, operated on with Blackwell's packed fp32x2
 // instructions (add/sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2).  A cpx<f2> is TWO complex numbers

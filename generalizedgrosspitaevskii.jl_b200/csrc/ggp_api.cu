@@ -321,10 +321,9 @@ struct PlanT : PlanBase {
   // TMA path of the strided kernel, per strided axis (1, 2)
   bool tma_ok[3] = {false, false, false};
   bool tma_d[3] = {false, false, false};  // exp_D staged by TMA as well
-#ifdef GGP_TMA
   CUtensorMap tmap[3][2];
   CUtensorMap dmap[3][4];
-#endif
+  bool tma_persistent = false;  // opt-in: the older persistent TMA kernel (make TMA=1, GGP_TMA_PERSISTENT=1)
   int sm_count = 148;
 
   ~PlanT() override {
@@ -577,6 +576,22 @@ struct PlanT : PlanBase {
       if (d.pump_ncomp != 1 && d.pump_ncomp != M) return fail(GGP_ERR_INVALID, "pump_ncomp must be 1 or ncomp");
       if ((rc = upload_table(d.pump_table, d.table_precision, d.pump_ncomp, 1.0, S))) return rc;
       pw.pump = d.pump_ncomp == 1 ? 1 : 2;
+      {  // spatially constant profile: keep the value in the kernel parameters
+        bool cst = true;
+        std::complex<double> v0[2];
+        for (int c = 0; c < d.pump_ncomp && cst; ++c)
+          for (long long i = 0; i < nspatial && cst; ++i) {
+            std::complex<double> z;
+            if (d.table_precision == GGP_C128) z = ((const std::complex<double>*)d.pump_table)[i * d.pump_ncomp + c];
+            else { const std::complex<float> f = ((const std::complex<float>*)d.pump_table)[i * d.pump_ncomp + c]; z = std::complex<double>(f.real(), f.imag()); }
+            if (i == 0) v0[c] = z;
+            else if (z != v0[c]) cst = false;
+          }
+        if (cst && !getenv("GGP_NO_PUMP_CONST")) {
+          pw.pump_const = 1;
+          for (int c = 0; c < d.pump_ncomp; ++c) pw.S_const[c] = mk<T>((T)v0[c].real(), (T)v0[c].imag());
+        }
+      }
       pw.S[0] = S[0];
       pw.S[1] = S[1];
       amp_prev = std::complex<double>(d.pump_amp0[0], d.pump_amp0[1]);
@@ -619,10 +634,12 @@ struct PlanT : PlanBase {
     cudaDeviceProp prop;
     GGP_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
+    // Tensor maps for the TMA staging of the strided kernel (StrParams::tma).  GGP_NO_TMA=1: plain LDG/STG.
+    // (The older persistent TMA kernel, str_tma.cuh, needs make TMA=1 and GGP_TMA_PERSISTENT=1.)
+    if (getenv("GGP_NO_TMA") || slab) return 0;
 #ifdef GGP_TMA
-    // The TMA-fed persistent variant is opt-in (GGP_TMA=1): with 32-byte box rows (W = 4 complex64) it
-    // measured slower than the LDG variant at two CTAs per SM on C2 (profiles/r01_notes.md).
-    if (!getenv("GGP_TMA") || getenv("GGP_NO_TMA") || slab) return 0;
+    tma_persistent = getenv("GGP_TMA_PERSISTENT") != nullptr;
+#endif
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -639,7 +656,7 @@ struct PlanT : PlanBase {
       if (!W || !us) continue;
       const size_t esz = sizeof(cpx<T>);
       if ((size_t)W * esz < 16 || (n[0] * esz) % 16 != 0) continue;
-      const size_t smem = esz * ((size_t)M * n[ax] * W + (size_t)W * M * LS) + 16;
+      const size_t smem = esz * ((tma_persistent ? (size_t)M * n[ax] * W : 0) + (size_t)W * M * LS) + 16;
       if (smem > (size_t)prop.sharedMemPerBlockOptin) continue;
       const cuuint32_t rows = (cuuint32_t)(n[ax] < 256 ? n[ax] : 256);
       bool ok = true;
@@ -658,7 +675,7 @@ struct PlanT : PlanBase {
       // exp_D planes through TMA as well when the shared memory budget allows (only the axis that multiplies)
       const int nplanes = ncols_of(dkind, M);
       const bool last_axis = ax == ndim - 1;
-      if (ok && last_axis && nplanes > 0 && !getenv("GGP_NO_TMA_D")) {
+      if (ok && tma_persistent && last_axis && nplanes > 0 && !getenv("GGP_NO_TMA_D")) {
         const size_t smem_d = smem + esz * (size_t)nplanes * n[ax] * W;
         if (smem_d <= (size_t)prop.sharedMemPerBlockOptin) {
           bool okd = true;
@@ -677,7 +694,6 @@ struct PlanT : PlanBase {
         }
       }
     }
-#endif
     return 0;
   }
 
@@ -811,8 +827,13 @@ struct PlanT : PlanBase {
     }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
+    if (tma_ok[ax] && !slab && !yslab && !scatter && !tma_persistent) {
+      p.tma = 1;
+      p.ax = ax;
+      for (int c = 0; c < M; ++c) p.map[c] = tmap[ax][c];
+    }
 #ifdef GGP_TMA
-    if (tma_ok[ax] && !slab) {
+    if (tma_ok[ax] && !slab && tma_persistent) {
       StrTmaParams<T> q;
       memset(&q, 0, sizeof(q));
       for (int c = 0; c < M; ++c) q.map[c] = tmap[ax][c];

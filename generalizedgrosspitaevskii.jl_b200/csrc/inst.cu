@@ -27,7 +27,8 @@ static int set_smem(KernelT k, size_t bytes) {
 // counter-productive (1024^2: 24.7 -> 29.8 us/step: the early CTAs land wherever a slot frees first and
 // unbalance the SMs), so those launch the plain way.  GGP_NO_PDL=1 / GGP_PDL=1 force it off / on.
 template <typename P>
-static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const P& p) {
+static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const P& p,
+                      unsigned cluster = 1) {
   static const int mode = getenv("GGP_NO_PDL") ? 0 : (getenv("GGP_PDL") ? 2 : 1);
   const bool pdl = mode == 2 || (mode == 1 && (unsigned long long)grid * block >= 148ull * 1024ull);
   cudaLaunchConfig_t cfg;
@@ -36,11 +37,23 @@ static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t 
   cfg.blockDim = dim3(block, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1 && grid % cluster == 0) {
+    // co-schedule the CTAs of adjacent fast-axis tiles: their 32-byte row pieces share DRAM pages
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
 
@@ -127,13 +140,32 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   p.logW = ilog2(W);
   p.LS = K::str_ls(W);
   p.ntx = nfast / W;
-  const size_t smem = K::USES_SMEM ? (size_t)W * M * p.LS * sizeof(cpx<T>) : 0;
+  size_t smem = K::USES_SMEM ? K::str_lines_bytes(M, W, p.LS) : 0;
+  if (K::str_tw_smem(M)) smem += K::TW_BYTES;  // twiddle table behind the exchange lines (compile-time decision)
+  // separable exp_D: stage D_line behind that if it does not cost a resident CTA
+  p.dl_smem = 0;
+  if (K::USES_SMEM && p.mode == 1 && p.dkind == KIND_SEP && !getenv("GGP_NO_DL_SMEM")) {
+    const size_t with_dl = smem + (((size_t)N * sizeof(cpx<T>) + 15) & ~(size_t)15);
+    const size_t per_sm = 227 * 1024 - 1024;
+    const int nb = K::str_min_blocks(M);
+    if ((with_dl + 1024) * (size_t)nb <= per_sm) {
+      p.dl_smem = 1;
+      smem = with_dl;
+    }
+  }
+  if (!K::USES_SMEM) p.tma = 0;
+  if (p.tma) {
+    smem = (smem + 15) & ~(size_t)15;
+    p.mbar_off = (int)smem;
+    smem += 16;
+  }
   const long long grid = p.ntx * nother;
   if (grid > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
   auto k = str_kernel<T, N, M>;
   int e = set_smem(k, smem);
   if (e) return e;
-  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p);
+  static const unsigned cl = getenv("GGP_STR_CLUSTER") ? (unsigned)atoi(getenv("GGP_STR_CLUSTER")) : 1u;
+  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p, cl);
 }
 
 template <typename T, int N>

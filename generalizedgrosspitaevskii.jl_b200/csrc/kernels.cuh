@@ -13,6 +13,7 @@
 #include <type_traits>
 #include "fft_line.cuh"
 #include "pointwise.cuh"
+#include "tma.cuh"
 
 #define GGP_MAX_PEERS 8
 
@@ -31,7 +32,12 @@ struct RowParams {
 };
 
 template <typename T>
-struct StrParams {
+struct alignas(64) StrParams {
+  // TMA staging (tma != 0): the tile [W complex] x [N rows] of every component is fetched by the TMA engine
+  // (boxes of <= 256 rows) into the shared-memory lines that afterwards serve as the exchange buffer, and the
+  // result leaves the same way.  rank-4 tensor [2*n1 reals, n2, n3, batch]; ax = which dimension the line runs along.
+  CUtensorMap map[2];
+  int tma, ax, mbar_off;  // mbar_off: byte offset of the mbarrier in dynamic shared memory (set by the launcher)
   cpx<T>* u[2];
   const typename TwT<T>::type* tw;
   long long ls;      // stride (elements) between consecutive points of a line
@@ -51,6 +57,7 @@ struct StrParams {
   cpx<T>* dst[GGP_MAX_PEERS][2];
   long long dst_ls, dst_s1, dst_s2, dst_base;
   int scatter, dst_shift;
+  int dl_smem;  // KIND_SEP: D_line is staged in shared memory behind the exchange lines (set by the launcher)
 };
 
 template <typename T>
@@ -101,8 +108,36 @@ struct KCfg {
   __host__ __device__ static constexpr int str_min_blocks(int M) {
     return data_regs(M) <= 32 ? 1024 / STR_THREADS : 1;
   }
+  // strided kernel: the twiddle table lives in shared memory (copied with cp.async at kernel start) whenever
+  // that does not cost a resident CTA.  Read from global memory at the point of use -- the 64-register budget
+  // leaves no room to batch the loads -- the ~60 twiddle loads per thread were serialised L1/L2 round trips and
+  // the critical path of the CTA (ncu r01n, 4096^2: 65 % of the stall samples long_scoreboard on them).
+  static constexpr int TW_COUNT = twiddle_count<T, N>();
+  static constexpr size_t TW_BYTES = ((size_t)TW_COUNT * sizeof(typename TwT<T>::type) + 15) & ~(size_t)15;
+  __host__ __device__ static constexpr size_t str_lines_bytes(int M, int W, int LS) {
+    return (((size_t)W * M * LS * sizeof(cpx<T>)) + 15) & ~(size_t)15;
+  }
+  __host__ __device__ static constexpr int str_ls_c(int W) {  // constexpr twin of str_ls
+    int lpg = W >= G ? 1 : G / W;
+    int ls = L::PADN;
+    while (ls % G != lpg % G) ++ls;
+    return ls;
+  }
+  // (only together with room for a staged D_line: with the twiddles alone in shared memory the L1 that is left
+  //  cannot hold D_line any more and its loads become the serialised round trips -- 4096^2 c64: 211 -> 248 us)
+  __host__ __device__ static constexpr bool str_tw_smem(int M) {
+    return USES_SMEM && TW_COUNT > 0 &&
+           (str_lines_bytes(M, WDEF, str_ls_c(WDEF)) + TW_BYTES + (size_t)N * sizeof(cpx<T>) + 1024) *
+                   (size_t)str_min_blocks(M) <= (size_t)226 * 1024;
+  }
+  // The register budget is stated explicitly for every variant: left to itself with "at least one CTA" the
+  // compiler spends 144 registers on the stochastic fp64 kernel (3 CTAs per SM instead of 4 at 128) and 190 on
+  // the two-component fp64 one (2 instead of 3 at 168) -- measured 17 % slower on C4 and C3.
   __host__ __device__ static constexpr int row_min_blocks(int M, int pwv) {
-    return (data_regs(M) <= 32 && pwv != PW_STOCH) ? 1024 / ROW_THREADS : 1;
+    const int dr = data_regs(M);
+    const int budget = dr <= 32 ? (pwv == PW_STOCH ? 128 : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pwv == PW_STOCH ? 255 : 168) : 255);
+    const int b = 65536 / (ROW_THREADS * budget);
+    return b < 1 ? 1 : b;
   }
   using RowSync = typename std::conditional<(TPL <= 32), SyncWarp, SyncBlock>::type;
 };
@@ -239,11 +274,21 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
 // mode 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
 template <typename T, int N, int M>
 __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_blocks(M))
-    str_kernel(const StrParams<T> p) {
+    str_kernel(const __grid_constant__ StrParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ROWS = N < 256 ? N : 256;  // rows per TMA box (boxDim <= 256)
+  extern __shared__ __align__(128) unsigned char smem_str_raw[];
+  unsigned char* const smem_raw = smem_str_raw;
   cpx<T>* smem = reinterpret_cast<cpx<T>*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + p.mbar_off);
+  if (p.tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   const int xw = threadIdx.x & (p.W - 1), t = threadIdx.x >> p.logW;
   const long long g = blockIdx.x;
@@ -254,34 +299,95 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_b
   const long long mstride = (long long)TPL * p.ls;
   cpx<T>* sl = smem + (size_t)xw * M * p.LS;
 
+  // Separable exp_D: the per-column factor is fetched now and D_line is copied into shared memory with
+  // cp.async while the field loads and the forward transform run -- both are constant tables, so this happens
+  // BEFORE the wait on the previous kernel.  (Read at the point of use, the 16 D_line loads per thread were
+  // the largest stall of this kernel: ncu r01m, 4096^2: long_scoreboard 41 % of the samples.)
+  // shared memory: [exchange lines | twiddle table (TW_SMEM) | D_line (dl_smem) | mbarrier (tma)]
+  constexpr bool TW_SMEM = K::str_tw_smem(M);
+  using Tw = typename TwT<T>::type;
+  unsigned char* const after_lines = smem_raw + K::str_lines_bytes(M, p.W, p.LS);
+  const Tw* twp = p.tw;
+  if constexpr (TW_SMEM) {
+    constexpr int NCHUNK = (int)(K::TW_BYTES / 16);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(after_lines);
+    for (int i = threadIdx.x; i < NCHUNK; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i),
+                   "l"(reinterpret_cast<const char*>(p.tw) + 16 * (size_t)i));
+    asm volatile("cp.async.commit_group;");
+    twp = reinterpret_cast<const Tw*>(after_lines);
+  }
+  const bool sep = p.mode == 1 && p.dkind == KIND_SEP;
+  cpx<T>* sdl = reinterpret_cast<cpx<T>*>(after_lines + (TW_SMEM ? K::TW_BYTES : 0));
+  cpx<T> dperp = mk<T>((T)1, (T)0);
+  if (sep) {
+    if constexpr (!TwT<T>::split) {
+      if (p.dl_smem) {
+        constexpr int NCHUNK = N * (int)sizeof(cpx<T>) / 16;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdl);
+        for (int i = threadIdx.x; i < NCHUNK; i += blockDim.x)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i),
+                       "l"(reinterpret_cast<const char*>(p.D[1]) + 16 * (size_t)i));
+        asm volatile("cp.async.commit_group;");
+      }
+      dperp = p.D[0][toff - (long long)t * p.ls];
+    }
+  }
   pdl_launch_dependents();
   pdl_wait();
   cpx<T> v[M][E];
+  if (p.tma) {
+    // one thread asks the TMA engine for the whole tile, dense [component][row][W] at the start of the
+    // exchange lines; everybody picks its elements up with conflict-free LDS -- the load/store unit sees 2
+    // wavefronts per 32 elements instead of one per 32-byte row piece (8 with W = 4, 16 with W = 2)
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)(M * N * p.W * sizeof(cpx<T>)));
+#pragma unroll 1
+      for (int c = 0; c < M; ++c)
+#pragma unroll 1
+        for (int r0 = 0; r0 < N; r0 += ROWS)
+          tma_load_4d(smem + ((size_t)c * N + r0) * p.W, &p.map[c], bar, (int)(2 * xt * p.W), p.ax == 1 ? r0 : (int)o1,
+                      p.ax == 1 ? (int)o1 : r0, (int)o2);
+    }
+    mbar_wait(bar, 0);
 #pragma unroll
-  for (int c = 0; c < M; ++c)
+    for (int c = 0; c < M; ++c)
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[c][m] = p.u[c][off + m * mstride];
+      for (int m = 0; m < E; ++m) v[c][m] = smem[(((size_t)c * N + t + m * TPL) << p.logW) + xw];
+  } else {
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[c][m] = p.u[c][off + m * mstride];
+  }
+  if (TW_SMEM || (sep && p.dl_smem)) asm volatile("cp.async.wait_all;" ::: "memory");  // published by the barriers of the transform
 
   const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
 #pragma unroll 1
   for (int it = it0; it <= it1; ++it) {
-    fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, p.tw, it == 1);
+    fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, twp, it == 1);
     if (it == 0 && p.mode == 1) {
       if (p.dkind == KIND_SEP) {
         if constexpr (TwT<T>::split) {
-          // fp32: both factors carry their rounding residual (hi + lo) and are applied one after the other
-          // with compensated products -- a table rounded to fp32 is a fixed per-mode error that adds up
-          // linearly over the steps of a run (see TwT in cplx.cuh)
-          const typename TwT<T>::type dperp = p.Dsp[0][toff - (long long)t * p.ls];
+          // fp32 with -DGGP_SPLIT_TWIDDLES: both factors carry their rounding residual (hi + lo) and are applied
+          // one after the other with compensated products (see TwT in cplx.cuh)
+          const typename TwT<T>::type dp = p.Dsp[0][toff - (long long)t * p.ls];
           const typename TwT<T>::type* dline = p.Dsp[1] + t;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
             const typename TwT<T>::type dl = dline[m * TPL];
 #pragma unroll
-            for (int c = 0; c < M; ++c) v[c][m] = TwT<T>::mul(TwT<T>::mul(v[c][m], dl), dperp);
+            for (int c = 0; c < M; ++c) v[c][m] = TwT<T>::mul(TwT<T>::mul(v[c][m], dl), dp);
+          }
+        } else if (p.dl_smem) {
+          const cpx<T>* dline = sdl + t;
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const cpx<T> d = cmul(dperp, dline[m * TPL]);
+#pragma unroll
+            for (int c = 0; c < M; ++c) v[c][m] = cmul(d, v[c][m]);
           }
         } else {
-          const cpx<T> dperp = p.D[0][toff - (long long)t * p.ls];
           const cpx<T>* dline = p.D[1] + t;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
@@ -313,6 +419,25 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_b
         const int j = t + m * TPL;
         p.dst[j >> p.dst_shift][c][dbase + (long long)(j & mask) * p.dst_ls] = v[c][m];
       }
+    return;
+  }
+  if (p.tma) {
+    __syncthreads();  // the last pass has read its inputs from the exchange lines
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int m = 0; m < E; ++m) smem[(((size_t)c * N + t + m * TPL) << p.logW) + xw] = v[c][m];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+      for (int c = 0; c < M; ++c)
+#pragma unroll 1
+        for (int r0 = 0; r0 < N; r0 += ROWS)
+          tma_store_4d(&p.map[c], smem + ((size_t)c * N + r0) * p.W, (int)(2 * xt * p.W), p.ax == 1 ? r0 : (int)o1,
+                       p.ax == 1 ? (int)o1 : r0, (int)o2);
+      tma_store_commit_and_wait_read();
+    }
     return;
   }
 #pragma unroll

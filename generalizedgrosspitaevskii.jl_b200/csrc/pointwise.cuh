@@ -33,6 +33,8 @@ struct PointwiseParams {
   const cpx<T>* S[2];
   int vkind;   // KIND_*
   int pump;    // 0 none, 1 scalar broadcast (S[0] for every component), 2 per component
+  int pump_const;      // the pump profile is the same at every grid point (e.g. examples/truncated_wigner.jl:37-39):
+  cpx<T> S_const[2];   // its value rides in the parameters and the table is not read
   int nl;      // 0 none, 1 real coefficients, 2 complex coefficients
   T nl_c_re[2], nl_c_im[2];
   T nl_g_re[2][2], nl_g_im[2][2];
@@ -88,7 +90,11 @@ __device__ __forceinline__ void sincosm1_t(double a, double* s, double* cm1) {
 // u + (cm1 + i s) u  =  (cos a + i sin a) u
 template <typename T>
 __device__ __forceinline__ cpx<T> rotate_m1(cpx<T> u, T cm1, T s) {
+#ifdef GGP_OLD_ROT
+  return cmul(mk<T>(cm1 + (T)1, s), u);
+#else
   return mk<T>(fma_(cm1, u.x, fnma_(s, u.y, u.x)), fma_(cm1, u.y, fma_(s, u.x, u.y)));
+#endif
 }
 __device__ __forceinline__ float expm1_t(float a) { return expm1f(a); }
 __device__ __forceinline__ double expm1_t(double a) { return expm1(a); }
@@ -193,7 +199,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
   if (p.pump) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      sv[j] = p.S[p.pump == 1 ? 0 : j][sidx];
+      sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j] : p.S[p.pump == 1 ? 0 : j][sidx];
       w[j] = f[j] + cmul(h.fnow, sv[j]);
     }
   } else {
