@@ -255,9 +255,10 @@ def measure(G, name, steps, warmup, device, nbatch=None, batch_offset=0, do_e2e=
         while done < steps:
             k = min(sps, steps - done)
             it.advance(k)
-            it.fetch()
+            it.save_async(0)          # streaming save: device snapshot + PCIe transfer overlapped with the next interval
             done += k
             d2h += 1
+        it.save_wait()                # the last saved state has landed in page-locked host memory
         el = time.perf_counter() - t0
         windows.append((tw0, time.time()))
         sbytes = sum(x.nbytes for x in u0)
@@ -447,7 +448,8 @@ def main():
                          h2d_bytes_per_step=res["e2e"]["h2d_bytes_per_step"],
                          d2h_bytes_per_step=res["e2e"]["d2h_bytes_per_step"],
                          what="pinned host u0 -> ggp_set_state, ggp_step in save intervals of <=1000 steps, "
-                              "ggp_get_state to pinned host after each (solve! of the host interface); plan creation excluded"),
+                              "ggp_save_async of the state to pinned host after each + final ggp_save_wait (solve! of the "
+                              "host interface); plan creation excluded"),
                 gpu_launches=res["launches"])
     windows = list(res["windows"])
     res["iter"].close()

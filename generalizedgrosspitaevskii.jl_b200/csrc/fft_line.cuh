@@ -24,13 +24,16 @@ struct IsPacked<f2> {
 };
 template <typename T>
 __host__ __device__ constexpr int default_E(int N) {
-  // fp32 (and the packed pairs): radix 16, radix 32 only where a line would otherwise need more than 256
-  // threads; fp64: radix 8, radix 16 likewise -- never wider than 64 data registers per component
+  // fp32 (and the packed pairs): radix 16, radix 32 only where a line would otherwise need more than 512
+  // threads; fp64: radix 8, radix 16 where a line would otherwise need more than 256 -- never wider than 64 data registers per component
   // (radix-32 fp64 = 128 data registers spills), so the longest fp64 lines take 512 threads instead.
   const bool f32 = sizeof(T) == 4 || IsPacked<T>::value;
   int e = f32 ? 16 : 8;
   const int emax = f32 ? 32 : 16;
-  while (N / e > 256 && e < emax) e *= 2;
+  // fp32 lines may take up to 512 threads: radix 32 for N = 8192 needed 151 registers in the row kernel (one
+  // 256-thread CTA = 8 warps per SM); radix 16 with 512 threads keeps 64 registers and 32 warps per SM
+  // (8192^2: row 626 -> 467 us, strided 1230 -> 1067 us, profiles/r01_notes.md session 4)
+  while (N / e > (f32 ? 512 : 256) && e < emax) e *= 2;
   return e < N ? e : N;
 }
 
@@ -63,9 +66,34 @@ __host__ __device__ constexpr int twiddle_count(int NS = 1) {
   return (NS > 1 ? (R - 1) * NS : 0) + twiddle_count<T, N>(NS * R);
 }
 
+// Long lines (N >= 4096): the late passes (NS >= 256) need (R-1)*NS twiddles -- a table as large as the line
+// itself, re-read by every CTA for every tile (4096: 30 KB per transform next to 64 KB of tile data; ncu r01r:
+// 45 % of the strided kernel's stall samples wait for these loads, L1 hit rate 38 %).  With FACT the twiddle is
+// formed on the fly instead,  w_N^j = A[j >> 6] * B[j & 63]  (two tables of N/64 and 64 entries, both exact to the
+// plan's precision, one extra complex multiply), and only the early passes' small blocks stay a table.
+// Compact table layout (host, ggp_api.cu):  twc[0..63] = B[j] = w_N^j,  twc[64 + j] = A[j] = w_N^(64 j).
+constexpr int TWF_LO = 64;
+constexpr int TWF_MIN_NS = 256;
+template <typename T, int N>
+__host__ __device__ constexpr bool tw_factorized() {
+  return N >= 4096 && !TwT<T>::split;
+}
+template <typename T, int N>
+__host__ __device__ constexpr int twiddle_compact_count() {
+  return tw_factorized<T, N>() ? TWF_LO + N / TWF_LO : 0;
+}
+// entries of the passes with NS < TWF_MIN_NS: a prefix of the table (the blocks are stored in pass order)
+template <typename T, int N>
+__host__ __device__ constexpr int twiddle_small_count(int NS = 1) {
+  constexpr int E = default_E<T>(N);
+  if (NS >= N || NS >= TWF_MIN_NS) return 0;
+  const int R = (N / NS >= E) ? E : N / NS;
+  return (NS > 1 ? (R - 1) * NS : 0) + twiddle_small_count<T, N>(NS * R);
+}
+
 // Stockham pass (NS = product of the radices of the earlier passes) and all later passes.
 // DIR = -1 forward (e^{-i k x}), +1 inverse (unnormalised); TWOFF = offset of this pass' twiddles.
-template <typename T, int N, int DIR, typename SYNC, int NS, int TWOFF = 0>
+template <typename T, int N, int DIR, typename SYNC, int NS, int TWOFF = 0, bool FACT = false>
 struct Passes {
   using Cfg = LineCfg<T, N>;
   static constexpr int E = Cfg::E;
@@ -75,7 +103,8 @@ struct Passes {
   static constexpr bool LASTP = (NS * R == N);
 
   static __device__ __forceinline__ void run(cpx<T> (&v)[E], const int t, cpx<T>* __restrict__ line,
-                                             const typename TwT<T>::type* __restrict__ tw) {
+                                             const typename TwT<T>::type* __restrict__ tw,
+                                             const typename TwT<T>::type* __restrict__ twc = nullptr) {
     if constexpr (NS > 1) {
       if constexpr (TPL % E == 0) {
         // pad(t + m*TPL) = pad(t) + m*(TPL + TPL/E): one base, immediate offsets
@@ -97,9 +126,18 @@ struct Passes {
       const int k = b & (NS - 1);
       if constexpr (NS > 1) {
         static_assert(DIR < 0, "the inverse transform runs the forward code on conjugated data");
-        const typename TwT<T>::type* twk = tw + TWOFF + k;
+        if constexpr (FACT && NS >= TWF_MIN_NS && tw_factorized<T, N>()) {
+          const int ks = k * (N / (NS * R));  // w_{NS R}^(r k) = w_N^(r ks)
 #pragma unroll
-        for (int r = 1; r < R; ++r) a[r] = TwT<T>::mul(a[r], twk[(r - 1) * NS]);
+          for (int r = 1; r < R; ++r) {
+            const int j = r * ks;
+            a[r] = cmul(a[r], cmul(twc[TWF_LO + (j >> 6)], twc[j & (TWF_LO - 1)]));
+          }
+        } else {
+          const typename TwT<T>::type* twk = tw + TWOFF + k;
+#pragma unroll
+          for (int r = 1; r < R; ++r) a[r] = TwT<T>::mul(a[r], twk[(r - 1) * NS]);
+        }
       }
       Dft<T, R, DIR>::run(a);
       if constexpr (LASTP) {
@@ -125,18 +163,19 @@ struct Passes {
     }
     if constexpr (!LASTP) {
       SYNC::sync();
-      Passes<T, N, DIR, SYNC, NS * R, TWOFF + (NS > 1 ? (R - 1) * NS : 0)>::run(v, t, line, tw);
+      Passes<T, N, DIR, SYNC, NS * R, TWOFF + (NS > 1 ? (R - 1) * NS : 0), FACT>::run(v, t, line, tw, twc);
     }
   }
 };
 
 // Transform one line held in registers.  PRESYNC: the shared line may still be read by a previous
 // transform of the same thread group, so synchronise before the first scatter.
-template <typename T, int N, int DIR, typename SYNC, bool PRESYNC>
+template <typename T, int N, int DIR, typename SYNC, bool PRESYNC, bool FACT = false>
 __device__ __forceinline__ void fft_line(cpx<T> (&v)[LineCfg<T, N>::E], const int t, cpx<T>* __restrict__ line,
-                                         const typename TwT<T>::type* __restrict__ tw) {
+                                         const typename TwT<T>::type* __restrict__ tw,
+                                         const typename TwT<T>::type* __restrict__ twc = nullptr) {
   if (PRESYNC && LineCfg<T, N>::E < N) SYNC::sync();
-  Passes<T, N, DIR, SYNC, 1>::run(v, t, line, tw);
+  Passes<T, N, DIR, SYNC, 1, 0, FACT>::run(v, t, line, tw, twc);
 }
 
 }  // namespace ggp

@@ -96,12 +96,12 @@ static int dispatch_str_tma(int N, int M, const StrTmaParams<T>& p, long long nf
 }
 #endif
 template <typename T>
-static void dispatch_str_query(int N, long long nfast, int* W, int* LS, int* threads, int* us) {
+static void dispatch_str_query(int N, int M, long long nfast, int* W, int* LS, int* threads, int* us) {
   *W = 0;
   switch (N) {
 #define X(n)                                   \
   case n:                                      \
-    str_query<T, n>(nfast, W, LS, threads, us); \
+    str_query<T, n>(M, nfast, W, LS, threads, us); \
     return;
     GGP_SIZES(X)
 #undef X
@@ -217,6 +217,11 @@ struct PlanBase {
   virtual void* state_ptr(int c) = 0;
   virtual int ipc_export(void* blob) = 0;
   virtual int ipc_attach(const void* blobs) = 0;
+  virtual int save_async(void* const* u) = 0;
+  virtual int save_wait() = 0;
+  virtual int64_t checkpoint_bytes() = 0;
+  virtual int checkpoint_save(void* blob, uint64_t capacity) = 0;
+  virtual int checkpoint_load(const void* blob, uint64_t size) = 0;
 
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -325,10 +330,21 @@ struct PlanT : PlanBase {
   CUtensorMap dmap[3][4];
   bool tma_persistent = false;  // opt-in: the older persistent TMA kernel (make TMA=1, GGP_TMA_PERSISTENT=1)
   int sm_count = 148;
+  // streaming saves: snapshot on the compute stream, device -> host on a copy stream
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t snap_ready = nullptr, copy_done = nullptr;
+  cpx<T>* snap[2] = {nullptr, nullptr};
+  bool copy_pending = false;
 
   ~PlanT() override {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) {
+      cudaStreamSynchronize(copy_stream);
+      cudaStreamDestroy(copy_stream);
+    }
+    if (snap_ready) cudaEventDestroy(snap_ready);
+    if (copy_done) cudaEventDestroy(copy_done);
     for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     for (void* p : allocs) cudaFree(p);
     if (flush_buf) cudaFree(flush_buf);
@@ -531,6 +547,19 @@ struct PlanT : PlanBase {
             NS *= R;
           }
           if (h.empty()) h.push_back(TwT<T>::make(1.0L, 0.0L));
+          // long lines: compact tables of the factorised twiddles behind the pass blocks (fft_line.cuh, FACT):
+          // [pad to an even count | B[j] = w_N^j, j < 64 | A[j] = w_N^(64 j), j < N/64]
+          if (N >= 4096 && !TwT<T>::split) {
+            if (h.size() % 2) h.push_back(TwT<T>::make(1.0L, 0.0L));
+            for (long long j = 0; j < TWF_LO; ++j) {
+              const long double ang = -twopi * (long double)j / (long double)N;
+              h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
+            }
+            for (long long j = 0; j < N / TWF_LO; ++j) {
+              const long double ang = -twopi * (long double)(j * TWF_LO) / (long double)N;
+              h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
+            }
+          }
         }
         if ((rc = dalloc((void**)&tw[a], sizeof(h[0]) * h.size()))) return rc;
         GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice));
@@ -650,9 +679,15 @@ struct PlanT : PlanBase {
       return 0;  // no TMA descriptors available: the LDG version of the kernel is used
     }
     EncodeFn encode = (EncodeFn)fn;
+    CUtensorMapL2promotion l2promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* e = getenv("GGP_TMA_L2PROMO")) {  // tuning knob: 0 / 64 / 128 / 256
+      const int v = atoi(e);
+      l2promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
     for (int ax = 1; ax < ndim; ++ax) {
       int W = 0, LS = 0, threads = 0, us = 0;
-      dispatch_str_query<T>((int)n[ax], n[0], &W, &LS, &threads, &us);
+      dispatch_str_query<T>((int)n[ax], M, n[0], &W, &LS, &threads, &us);
       if (!W || !us) continue;
       const size_t esz = sizeof(cpx<T>);
       if ((size_t)W * esz < 16 || (n[0] * esz) % 16 != 0) continue;
@@ -667,7 +702,7 @@ struct PlanT : PlanBase {
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmap[ax][c], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                             4, (void*)u[c], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, l2promo,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) ok = false;
       }
@@ -711,6 +746,98 @@ struct PlanT : PlanBase {
     return 0;
   }
   void* state_ptr(int c) override { return (c >= 0 && c < M) ? (void*)u[c] : nullptr; }
+
+  // ---- streaming saves (replaces `map(copy!, slice, iter.u)`, src/fixed_time_stepping.jl:48, without stalling the
+  // step chain): the state is snapshotted device-to-device on the compute stream (tens of microseconds), the slow
+  // PCIe transfer of the snapshot runs on a second stream while the next save interval is already stepping.
+  // One snapshot buffer: a new save waits (on the device, not on the host) for the previous transfer to drain.
+  int save_async(void* const* uh) override {
+    const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+    int rc;
+    if (!copy_stream) {
+      GGP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      GGP_CUDA(cudaEventCreateWithFlags(&snap_ready, cudaEventDisableTiming));
+      GGP_CUDA(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
+    }
+    for (int c = 0; c < M; ++c)
+      if (!snap[c] && (rc = dalloc((void**)&snap[c], bytes))) return rc;
+    if (copy_pending) GGP_CUDA(cudaStreamWaitEvent(stream, copy_done, 0));
+    for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(snap[c], u[c], bytes, cudaMemcpyDeviceToDevice, stream));
+    GGP_CUDA(cudaEventRecord(snap_ready, stream));
+    GGP_CUDA(cudaStreamWaitEvent(copy_stream, snap_ready, 0));
+    for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(uh[c], snap[c], bytes, cudaMemcpyDeviceToHost, copy_stream));
+    GGP_CUDA(cudaEventRecord(copy_done, copy_stream));
+    copy_pending = true;
+    return 0;
+  }
+  int save_wait() override {
+    if (copy_pending) {
+      GGP_CUDA(cudaEventSynchronize(copy_done));
+      copy_pending = false;
+    }
+    if (p2p) return barrier_status();
+    return 0;
+  }
+
+  // ---- checkpoint / resume (absent in the reference).  Everything a bit-identical continuation
+  // needs that is not in the descriptor: the fields, the half-step counter (Philox counter word and pump phase)
+  // and F_now's amplitude.  A restart from a saved slice alone is NOT identical because of the one-dt-late pump
+  // (quirk Q1) and the noise counters.
+  struct CkptHeader {
+    uint64_t magic;
+    uint32_t version, precision;
+    int32_t ndim, ncomp;
+    int64_t n[3], nbatch, batch_offset;
+    uint64_t half_ctr;
+    double amp_prev[2];
+    uint64_t bytes_per_comp;
+  };
+  static constexpr uint64_t CKPT_MAGIC = 0x54504b4350474721ull;  // "!GGPCKPT"
+  int64_t checkpoint_bytes() override {
+    return (int64_t)(sizeof(CkptHeader) + (size_t)M * sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch);
+  }
+  int checkpoint_save(void* blob, uint64_t capacity) override {
+    if ((int64_t)capacity < checkpoint_bytes()) return fail(GGP_ERR_INVALID, "checkpoint buffer too small (ggp_checkpoint_bytes)");
+    CkptHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = CKPT_MAGIC;
+    h.version = 1;
+    h.precision = sizeof(T) == 4 ? GGP_C64 : GGP_C128;
+    h.ndim = ndim;
+    h.ncomp = M;
+    for (int i = 0; i < 3; ++i) h.n[i] = n[i];
+    h.nbatch = nbatch;
+    h.batch_offset = batch_offset;
+    h.half_ctr = half_ctr;
+    h.amp_prev[0] = amp_prev.real();
+    h.amp_prev[1] = amp_prev.imag();
+    h.bytes_per_comp = sizeof(cpx<T>) * (uint64_t)nspatial * (uint64_t)nbatch;
+    memcpy(blob, &h, sizeof(h));
+    char* q = (char*)blob + sizeof(h);
+    for (int c = 0; c < M; ++c)
+      GGP_CUDA(cudaMemcpyAsync(q + (size_t)c * h.bytes_per_comp, u[c], h.bytes_per_comp, cudaMemcpyDeviceToHost, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int checkpoint_load(const void* blob, uint64_t size) override {
+    if (size < sizeof(CkptHeader)) return fail(GGP_ERR_INVALID, "checkpoint truncated");
+    CkptHeader h;
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != CKPT_MAGIC || h.version != 1) return fail(GGP_ERR_INVALID, "not a ggp checkpoint (magic/version)");
+    const bool same = h.precision == (uint32_t)(sizeof(T) == 4 ? GGP_C64 : GGP_C128) && h.ndim == ndim && h.ncomp == M &&
+                      h.n[0] == n[0] && h.n[1] == n[1] && h.n[2] == n[2] && h.nbatch == nbatch &&
+                      h.batch_offset == batch_offset &&
+                      h.bytes_per_comp == sizeof(cpx<T>) * (uint64_t)nspatial * (uint64_t)nbatch;
+    if (!same) return fail(GGP_ERR_INVALID, "checkpoint was written by a plan of a different shape / precision / shard");
+    if (size < sizeof(h) + (uint64_t)M * h.bytes_per_comp) return fail(GGP_ERR_INVALID, "checkpoint truncated");
+    const char* q = (const char*)blob + sizeof(h);
+    for (int c = 0; c < M; ++c)
+      GGP_CUDA(cudaMemcpyAsync(u[c], q + (size_t)c * h.bytes_per_comp, h.bytes_per_comp, cudaMemcpyHostToDevice, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    half_ctr = h.half_ctr;
+    amp_prev = std::complex<double>(h.amp_prev[0], h.amp_prev[1]);
+    return 0;
+  }
 
   // half-step `half` (0/1) of the step whose pump amplitudes are (a_now, a_next)
   HalfStep<T> make_half(std::complex<double> a_now, std::complex<double> a_next, int slot) {
@@ -1242,6 +1369,26 @@ int ggp_get_state(ggp_plan* p, void* const* u) {
   GGP_ENTER(p);
   if (!u) return fail(GGP_ERR_INVALID, "null state");
   return p->impl->get_state(u);
+}
+int ggp_save_async(ggp_plan* p, void* const* u) {
+  GGP_ENTER(p);
+  if (!u) return fail(GGP_ERR_INVALID, "null state");
+  return p->impl->save_async(u);
+}
+int ggp_save_wait(ggp_plan* p) {
+  GGP_ENTER(p);
+  return p->impl->save_wait();
+}
+int64_t ggp_checkpoint_bytes(ggp_plan* p) { return (p && p->impl) ? p->impl->checkpoint_bytes() : (int64_t)GGP_ERR_INVALID; }
+int ggp_checkpoint_save(ggp_plan* p, void* blob, uint64_t capacity) {
+  GGP_ENTER(p);
+  if (!blob) return fail(GGP_ERR_INVALID, "null blob");
+  return p->impl->checkpoint_save(blob, capacity);
+}
+int ggp_checkpoint_load(ggp_plan* p, const void* blob, uint64_t size) {
+  GGP_ENTER(p);
+  if (!blob) return fail(GGP_ERR_INVALID, "null blob");
+  return p->impl->checkpoint_load(blob, size);
 }
 int ggp_step(ggp_plan* p, int64_t nsteps, const double* amp, const void* const* noise) {
   GGP_ENTER(p);

@@ -83,12 +83,16 @@ int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
 }
 
 template <typename T, int N>
-void str_query(long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
+void str_query(int M, long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
   using K = KCfg<T, N>;
+  const int wmax = K::str_max_threads(M) / K::TPL;
   int W = K::WDEF;
+  // opt-in: one 1024-thread CTA per SM with twice the tile width -- measured slower (4096^2: 225 vs 208 us per
+  // pass, same DRAM traffic; profiles/r01_notes.md session 4)
+  if (wmax > W && getenv("GGP_STR_WIDE")) W = wmax;
   if (const char* e = getenv("GGP_STR_W")) {  // tuning knob
     const int w = atoi(e);
-    if (w >= 1 && w <= K::WDEF && (w & (w - 1)) == 0) W = w;
+    if (w >= 1 && w <= wmax && (w & (w - 1)) == 0) W = w;
   }
   while (W > nfast) W >>= 1;
   *W_ = W;
@@ -102,7 +106,7 @@ template <typename T, int N, int M>
 static int launch_str_tma_m(StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS, threads, us;
-  str_query<T, N>(nfast, &W, &LS, &threads, &us);
+  str_query<T, N>(M, nfast, &W, &LS, &threads, &us);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = LS;
@@ -135,19 +139,29 @@ template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS_, threads_, us_;
-  str_query<T, N>(nfast, &W, &LS_, &threads_, &us_);
+  str_query<T, N>(M, nfast, &W, &LS_, &threads_, &us_);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = K::str_ls(W);
   p.ntx = nfast / W;
   size_t smem = K::USES_SMEM ? K::str_lines_bytes(M, W, p.LS) : 0;
-  if (K::str_tw_smem(M)) smem += K::TW_BYTES;  // twiddle table behind the exchange lines (compile-time decision)
+  // CTAs per SM the register file allows with this geometry (the launch bounds cap the registers accordingly)
+  int nb = K::str_min_blocks(M);
+  if (W * K::TPL > K::STR_THREADS) nb = K::str_bound_blocks(M);
+  const size_t per_sm = 227 * 1024 - 1024;
+  const size_t dl_bytes = (((size_t)N * sizeof(cpx<T>) + 15) & ~(size_t)15);
+  p.tw_smem = 0;
+  if (K::str_tw_smem(M)) {
+    smem += K::TW_BYTES;  // twiddle table behind the exchange lines (compile-time decision)
+  } else if (K::USES_SMEM && K::TW_COUNT > 0 && !getenv("GGP_NO_TW_SMEM_RT") &&
+             (smem + K::TW_BYTES + dl_bytes + 1024) * (size_t)nb <= per_sm) {
+    p.tw_smem = 1;  // ... or decided here for a geometry chosen at run time (wide tiles of the long fp32 lines)
+    smem += K::TW_BYTES;
+  }
   // separable exp_D: stage D_line behind that if it does not cost a resident CTA
   p.dl_smem = 0;
   if (K::USES_SMEM && p.mode == 1 && p.dkind == KIND_SEP && !getenv("GGP_NO_DL_SMEM")) {
-    const size_t with_dl = smem + (((size_t)N * sizeof(cpx<T>) + 15) & ~(size_t)15);
-    const size_t per_sm = 227 * 1024 - 1024;
-    const int nb = K::str_min_blocks(M);
+    const size_t with_dl = smem + dl_bytes;
     if ((with_dl + 1024) * (size_t)nb <= per_sm) {
       p.dl_smem = 1;
       smem = with_dl;
@@ -246,6 +260,6 @@ template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaS
 #ifdef GGP_TMA
 template int launch_str_tma<GGP_T, GGP_N>(int, StrTmaParams<GGP_T>, long long, long long, int, cudaStream_t);
 #endif
-template void str_query<GGP_T, GGP_N>(long long, int*, int*, int*, int*);
+template void str_query<GGP_T, GGP_N>(int, long long, int*, int*, int*, int*);
 
 }  // namespace ggp

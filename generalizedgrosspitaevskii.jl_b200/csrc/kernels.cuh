@@ -58,6 +58,8 @@ struct alignas(64) StrParams {
   long long dst_ls, dst_s1, dst_s2, dst_base;
   int scatter, dst_shift;
   int dl_smem;  // KIND_SEP: D_line is staged in shared memory behind the exchange lines (set by the launcher)
+  int tw_smem;  // twiddle table staged in shared memory although the compile-time default (str_tw_smem) says no:
+                // set by the launcher when the geometry chosen at run time (W, CTAs per SM) leaves room for it
 };
 
 template <typename T>
@@ -98,7 +100,7 @@ struct KCfg {
   // 1024-thread CTA fills the register file alone and runs its load / transform / store phases in
   // lock-step with nothing to overlap them (4096^2 c64: 219 us per pass before, profiles/r01_notes.md).
   static constexpr int WMIN = sizeof(T) == 4 ? 4 : 2;
-  static constexpr int WCAP = (512 / TPL) < 1 ? 1 : (512 / TPL);
+  static constexpr int WCAP = (sizeof(T) == 4 && TPL == 512) ? 2 : ((512 / TPL) < 1 ? 1 : (512 / TPL));
   static constexpr int WWANT = (256 / TPL) < WMIN ? WMIN : ((256 / TPL) > 32 ? 32 : (256 / TPL));
   static constexpr int WDEF = WWANT < WCAP ? WWANT : WCAP;
   static constexpr int STR_THREADS = WDEF * TPL;
@@ -108,12 +110,29 @@ struct KCfg {
   __host__ __device__ static constexpr int str_min_blocks(int M) {
     return data_regs(M) <= 32 ? 1024 / STR_THREADS : 1;
   }
+  // Tuning headroom: the fp32 kernels that fit 64 registers may be launched with twice the tile width (1024
+  // threads, one CTA per SM; GGP_STR_WIDE=1).  Not the default: at 4096^2 the wide tile is slower (225 vs 208 us)
+  // and the DRAM traffic is the same 2x of the algorithmic bytes either way (ncu, profiles/r01_notes.md session 4).
+  __host__ __device__ static constexpr int str_max_threads(int M) {
+    return (sizeof(T) == 4 && data_regs(M) <= 32 && STR_THREADS == 512) ? 1024 : STR_THREADS;
+  }
+  __host__ __device__ static constexpr int str_bound_blocks(int M) {  // min CTAs per SM stated in the launch bounds
+    return str_max_threads(M) > STR_THREADS ? 1 : str_min_blocks(M);
+  }
   // strided kernel: the twiddle table lives in shared memory (copied with cp.async at kernel start) whenever
   // that does not cost a resident CTA.  Read from global memory at the point of use -- the 64-register budget
   // leaves no room to batch the loads -- the ~60 twiddle loads per thread were serialised L1/L2 round trips and
   // the critical path of the CTA (ncu r01n, 4096^2: 65 % of the stall samples long_scoreboard on them).
   static constexpr int TW_COUNT = twiddle_count<T, N>();
-  static constexpr size_t TW_BYTES = ((size_t)TW_COUNT * sizeof(typename TwT<T>::type) + 15) & ~(size_t)15;
+  // long lines: the strided kernel forms the late passes' twiddles from the compact tables (fft_line.cuh, FACT) and
+  // stages only the early passes' blocks + the compact tables: 3 KB instead of 33 KB for N = 4096
+  static constexpr bool FACT = tw_factorized<T, N>();
+  static constexpr int TW_SMALL = twiddle_small_count<T, N>();
+  static constexpr int TW_COMPACT = twiddle_compact_count<T, N>();
+  static constexpr int TW_COMPACT_OFF = (TW_COUNT + 1) & ~1;  // global table: [pass blocks | pad | compact tables]
+  static constexpr int TW_STAGED = FACT ? TW_SMALL + TW_COMPACT : TW_COUNT;
+  static_assert(!FACT || TW_SMALL % 2 == 0, "16-byte staging chunks");
+  static constexpr size_t TW_BYTES = ((size_t)TW_STAGED * sizeof(typename TwT<T>::type) + 15) & ~(size_t)15;
   __host__ __device__ static constexpr size_t str_lines_bytes(int M, int W, int LS) {
     return (((size_t)W * M * LS * sizeof(cpx<T>)) + 15) & ~(size_t)15;
   }
@@ -152,13 +171,14 @@ __device__ __forceinline__ void conj_all(cpx<T> (&v)[E]) {
 // on conjugated data (ifft(x) = conj(fft(conj(x)))), selected by a loop that is NOT unrolled.
 // This halves the instruction footprint -- the first version of these kernels was bound by
 // instruction-cache misses (ncu: stall_no_instructions dominant, profiles/r01_notes.md).
-template <typename T, int N, int M, typename SYNC>
+template <typename T, int N, int M, typename SYNC, bool FACT = false>
 __device__ __forceinline__ void fft_fwd_all(cpx<T> (&v)[M][LineCfg<T, N>::E], const int t, cpx<T>* sl, const int LS,
-                                            const typename TwT<T>::type* __restrict__ tw, const bool inverse) {
+                                            const typename TwT<T>::type* __restrict__ tw, const bool inverse,
+                                            const typename TwT<T>::type* __restrict__ twc = nullptr) {
 #pragma unroll
   for (int c = 0; c < M; ++c) {
     if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
-    fft_line<T, N, -1, SYNC, true>(v[c], t, sl + c * LS, tw);
+    fft_line<T, N, -1, SYNC, true, FACT>(v[c], t, sl + c * LS, tw, twc);
     if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
   }
 }
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
 
 // mode 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
 template <typename T, int N, int M>
-__global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_blocks(M))
+__global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::str_bound_blocks(M))
     str_kernel(const __grid_constant__ StrParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
@@ -308,17 +328,24 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_b
   using Tw = typename TwT<T>::type;
   unsigned char* const after_lines = smem_raw + K::str_lines_bytes(M, p.W, p.LS);
   const Tw* twp = p.tw;
-  if constexpr (TW_SMEM) {
-    constexpr int NCHUNK = (int)(K::TW_BYTES / 16);
+  const Tw* twc = p.tw + K::TW_COMPACT_OFF;
+  const bool tws = K::TW_STAGED > 0 && (TW_SMEM || p.tw_smem);
+  if (tws) {
+    // FACT: [early passes' blocks | compact tables] are two ranges of the global table, contiguous in shared memory
+    constexpr int NCH1 = (int)((size_t)(K::FACT ? K::TW_SMALL : K::TW_COUNT) * sizeof(Tw) / 16);
+    constexpr int NCH = (int)(K::TW_BYTES / 16);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(after_lines);
-    for (int i = threadIdx.x; i < NCHUNK; i += blockDim.x)
+    const char* g1 = reinterpret_cast<const char*>(p.tw);
+    const char* g2 = reinterpret_cast<const char*>(p.tw + K::TW_COMPACT_OFF) - (size_t)NCH1 * 16;
+    for (int i = threadIdx.x; i < NCH; i += blockDim.x)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i),
-                   "l"(reinterpret_cast<const char*>(p.tw) + 16 * (size_t)i));
+                   "l"((K::FACT && i >= NCH1 ? g2 : g1) + 16 * (size_t)i));
     asm volatile("cp.async.commit_group;");
     twp = reinterpret_cast<const Tw*>(after_lines);
+    twc = twp + K::TW_SMALL;
   }
   const bool sep = p.mode == 1 && p.dkind == KIND_SEP;
-  cpx<T>* sdl = reinterpret_cast<cpx<T>*>(after_lines + (TW_SMEM ? K::TW_BYTES : 0));
+  cpx<T>* sdl = reinterpret_cast<cpx<T>*>(after_lines + (tws ? K::TW_BYTES : 0));
   cpx<T> dperp = mk<T>((T)1, (T)0);
   if (sep) {
     if constexpr (!TwT<T>::split) {
@@ -360,12 +387,12 @@ __global__ void __launch_bounds__(KCfg<T, N>::STR_THREADS, KCfg<T, N>::str_min_b
 #pragma unroll
       for (int m = 0; m < E; ++m) v[c][m] = p.u[c][off + m * mstride];
   }
-  if (TW_SMEM || (sep && p.dl_smem)) asm volatile("cp.async.wait_all;" ::: "memory");  // published by the barriers of the transform
+  if (tws || (sep && p.dl_smem)) asm volatile("cp.async.wait_all;" ::: "memory");  // published by the barriers of the transform
 
   const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
 #pragma unroll 1
   for (int it = it0; it <= it1; ++it) {
-    fft_fwd_all<T, N, M, SyncBlock>(v, t, sl, p.LS, twp, it == 1);
+    fft_fwd_all<T, N, M, SyncBlock, K::FACT>(v, t, sl, p.LS, twp, it == 1, twc);
     if (it == 0 && p.mode == 1) {
       if (p.dkind == KIND_SEP) {
         if constexpr (TwT<T>::split) {
@@ -510,6 +537,6 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
 // geometry of the strided kernels for a fast axis of nfast points: W (coalescing width), padded
 // line stride LS, threads per CTA, and whether the line needs the shared exchange buffer
 template <typename T, int N>
-void str_query(long long nfast, int* W, int* LS, int* threads, int* uses_smem);
+void str_query(int M, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
 
 }  // namespace ggp

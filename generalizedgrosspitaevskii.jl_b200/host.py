@@ -429,6 +429,21 @@ def _ptr_array(arrs):
     return arr
 
 
+class _PinnedBlock:
+    """Owner of one ggp_host_alloc block; frees it when the NumPy array built on top of it dies."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.ggp_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class StrangSplittingIterator:
     def __init__(self, prob, tspan, *, dt, nsaves, save_start=True, rng=None, device=-1,
                  batch_offset=0, stream=None, slab=None, slab_local=False):
@@ -478,7 +493,8 @@ class StrangSplittingIterator:
             self.nbatch = int(prob.u0[0].size // nspatial)
             rg, dg = reciprocal_grid(prob), direct_grid(prob)
         self.u0_local = u0_local
-        self.result = tuple(np.stack([x] * (nsaves + self.save_start), axis=0) for x in u0_local)  # :41-43
+        self._result_shape = [(nsaves + self.save_start,) + tuple(x.shape) for x in u0_local]
+        self.result = None                                   # allocated page-locked once the library is up
 
         dkind, dtab = exp_table(prob.dispersion, rg, prob.param, self.dt, M)            # :53
         vkind, vtab = exp_table(prob.potential, dg, prob.param, self.dt / 2, M)         # :54
@@ -562,7 +578,15 @@ class StrangSplittingIterator:
         handle = C.c_void_p()
         L.check(lib.ggp_plan_create(C.byref(d), C.byref(handle)))
         self.handle = handle
-        self._pinned = []
+        # result[..., n] slices (src/strang_splitting.jl:41-43), every slot pre-filled with u0; page-locked so the
+        # streaming saves (ggp_save_async) overlap the next save interval.  Julia's trailing save index is the
+        # leading NumPy axis over the same memory.
+        res = []
+        for x, shp in zip(u0_local, self._result_shape):
+            r = self._pinned_empty(shp, x.dtype)
+            r[...] = x
+            res.append(r)
+        self.result = tuple(res)
         self.u = [self._pinned_like(x) for x in u0_local]                               # :48 (pinned staging)
         for dst, src in zip(self.u, u0_local):
             np.copyto(dst, src)
@@ -570,14 +594,20 @@ class StrangSplittingIterator:
         self._step_index = 0
 
     def _pinned_like(self, x):
-        """Page-locked host staging buffer (async DMA at full PCIe rate); plain NumPy if that fails."""
-        nbytes = int(x.size) * x.dtype.itemsize
-        ptr = self.lib.ggp_host_alloc(nbytes)
+        return self._pinned_empty(x.shape, x.dtype)
+
+    def _pinned_empty(self, shape, dtype):
+        """Page-locked host array (async DMA at full PCIe rate); plain NumPy if that fails.  The block is owned by
+        the array: it is released when the last view of it is garbage-collected, NOT by close() -- `solve`
+        hands `result` to the caller after the plan is gone."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        ptr = self.lib.ggp_host_alloc(nbytes) if nbytes else None
         if not ptr:
-            return np.empty(x.shape, dtype=x.dtype)
-        self._pinned.append(ptr)
+            return np.empty(shape, dtype=dtype)
         buf = (C.c_char * nbytes).from_address(ptr)
-        return np.frombuffer(buf, dtype=x.dtype).reshape(x.shape)
+        buf._ggp_owner = _PinnedBlock(self.lib, ptr)          # np.frombuffer keeps `buf` alive, `buf` keeps the block
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def upload(self, u0=None):
         """Host -> device copy of the state (`u = copy.(prob.u0)`, src/strang_splitting.jl:48)."""
@@ -591,9 +621,6 @@ class StrangSplittingIterator:
             self.lib.ggp_plan_destroy(self.handle)
             self.handle = None
             self.u = None
-            for ptr in self._pinned:
-                self.lib.ggp_host_free(ptr)
-            self._pinned = []
 
     def __del__(self):
         try:
@@ -622,6 +649,35 @@ class StrangSplittingIterator:
     def fetch(self):
         L.check(self.lib.ggp_get_state(self.handle, _ptr_array(self.u)))
         return self.u
+
+    def save_async(self, slot):
+        """Non-blocking `map(copy!, slice, iter.u)` into result[..., slot] (src/fixed_time_stepping.jl:48): device
+        snapshot in stream order, PCIe transfer on a second stream while the next interval steps (ggp_save_async)."""
+        L.check(self.lib.ggp_save_async(self.handle, _ptr_array([r[slot] for r in self.result])))
+
+    def save_wait(self):
+        L.check(self.lib.ggp_save_wait(self.handle))
+
+    # -- checkpoint / resume (SURVEY §8f N3) ---------------------------------------------------
+    def checkpoint(self):
+        """Bytes that continue this run bit-identically when given to `restore` of an iterator built from the same
+        problem / tspan / dt / nsaves: the library blob (fields, Philox counter word, F_now amplitude) followed by
+        the host-side position in the step / pump schedule."""
+        n = int(self.lib.ggp_checkpoint_bytes(self.handle))
+        if n < 0:
+            L.check(n)
+        buf = np.empty(n + 8, dtype=np.uint8)
+        L.check(self.lib.ggp_checkpoint_save(self.handle, buf.ctypes.data, n))
+        buf[n:] = np.frombuffer(np.int64(self._step_index).tobytes(), dtype=np.uint8)
+        return buf.tobytes()
+
+    def restore(self, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        n = int(self.lib.ggp_checkpoint_bytes(self.handle))
+        if buf.size != n + 8:
+            raise ValueError("checkpoint size does not match this problem")
+        L.check(self.lib.ggp_checkpoint_load(self.handle, buf.ctypes.data, n))
+        self._step_index = int(np.frombuffer(buf[n:].tobytes(), dtype=np.int64)[0])
 
     def observe(self, kind):
         shape = self.u[0].shape[self.u[0].ndim - self.prob.ndim:]
@@ -659,10 +715,9 @@ def solve_(it, noise_buffers=None):
         it.advance(sps, nb)                                  # :43-47 batched into one call
         for _ in range(sps):
             t = t + it.dt                                    # :44 (accumulated in T)
-        u = it.fetch()                                       # :48
-        for r, x in zip(it.result, u):
-            r[n + off] = x
+        it.save_async(n + off)                               # :48, overlapped with the next interval
         it.ts[n + 1] = t                                     # :49
+    it.save_wait()
     return it.ts[1 - off:], it.result                        # :53
 
 

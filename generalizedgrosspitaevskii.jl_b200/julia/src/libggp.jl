@@ -83,6 +83,28 @@ function ggp_get_state(h::Ptr{Cvoid}, dest::NTuple{M,Any}) where {M}
     GC.@preserve dest ptrs _check(ccall(_sym(:ggp_get_state), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), h, ptrs))
 end
 
+# Streaming save (include/ggp.h: ggp_save_async / ggp_save_wait): device snapshot in stream order, PCIe transfer
+# on a second stream while the next interval steps.  `dest` must stay alive until ggp_save_wait (solve! keeps
+# iter.result alive); page-locking it (cudaHostRegister through CUDA.jl, or ggp_host_alloc-backed arrays via
+# unsafe_wrap) makes the transfer truly asynchronous -- pageable memory still works, the copy then synchronises.
+function ggp_save_async(h::Ptr{Cvoid}, dest::NTuple{M,Any}) where {M}
+    ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(x)) for x in dest]
+    GC.@preserve dest ptrs _check(ccall(_sym(:ggp_save_async), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), h, ptrs))
+end
+ggp_save_wait(h::Ptr{Cvoid}) = _check(ccall(_sym(:ggp_save_wait), Cint, (Ptr{Cvoid},), h))
+
+# Checkpoint / resume (include/ggp.h): fields + Philox counter word + F_now amplitude as one byte vector
+function ggp_checkpoint(h::Ptr{Cvoid})
+    n = ccall(_sym(:ggp_checkpoint_bytes), Int64, (Ptr{Cvoid},), h)
+    n < 0 && _check(Cint(n))
+    blob = Vector{UInt8}(undef, n)
+    GC.@preserve blob _check(ccall(_sym(:ggp_checkpoint_save), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64), h, pointer(blob), n))
+    blob
+end
+function ggp_restore(h::Ptr{Cvoid}, blob::Vector{UInt8})
+    GC.@preserve blob _check(ccall(_sym(:ggp_checkpoint_load), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64), h, pointer(blob), length(blob)))
+end
+
 # amps: 2 x nsteps ComplexF64 (column s = [a(t_s + dt/2), a(t_s + dt)]) or nothing (static / no pump)
 function ggp_step(h::Ptr{Cvoid}, nsteps::Integer, amps::Union{Nothing,AbstractMatrix{ComplexF64}})
     if amps === nothing

@@ -113,7 +113,8 @@ function step!(iter::StrangSplittingIterator, t, dt)
 end
 
 # solve!: the reference's loop (src/fixed_time_stepping.jl:26-54) with the inner `for _ in 1:steps_per_save`
-# batched into one ggp_step call and `map(copy!, slice, iter.u)` replaced by one D2H per save.
+# batched into one ggp_step call and `map(copy!, slice, iter.u)` replaced by one streaming save per interval
+# (device snapshot + D2H on a second stream, overlapped with the next interval; one wait at the end).
 function solve!(iter::StrangSplittingIterator)
     save_start, sps, dt, p, ts = iter.save_start, iter.steps_per_save, iter.dt, iter.progress, iter.ts
     nd = ndims(first(iter.result))
@@ -127,9 +128,20 @@ function solve!(iter::StrangSplittingIterator)
             _next!(p)
         end
         slices = map(x -> selectdim(x, nd, n + save_start), iter.result)   # contiguous: last dim
-        ggp_get_state(iter.handle, slices)
+        ggp_save_async(iter.handle, slices)
         ts[n+1] = t
     end
+    ggp_save_wait(iter.handle)
     _finish!(p, iter.given_progress)
     ts[begin+1-save_start:end], iter.result
+end
+
+# Checkpoint / resume (SURVEY §8f N3; the reference has none).  `checkpoint(iter)` returns the bytes that let
+# `restore!(init(prob, alg, tspan; same kwargs...), blob)` continue bit-identically (fields, Philox counter word,
+# F_now amplitude, position in the pump schedule).
+checkpoint(iter::StrangSplittingIterator) = vcat(ggp_checkpoint(iter.handle), reinterpret(UInt8, [Int64(iter.step_index)]))
+function restore!(iter::StrangSplittingIterator, blob::Vector{UInt8})
+    ggp_restore(iter.handle, blob[1:end-8])
+    iter.step_index = Int(reinterpret(Int64, blob[end-7:end])[1])
+    iter
 end

@@ -164,6 +164,30 @@ int ggp_step(ggp_plan *plan, int64_t nsteps, const double *pump_amp, const void 
 
 int ggp_synchronize(ggp_plan *plan);
 
+/*
+ * Streaming save: the non-blocking form of ggp_get_state for the snapshot copy of solve!'s
+ * save loop, `map(copy!, slice, iter.u)` (src/fixed_time_stepping.jl:48).  The state is snapshotted on the
+ * device in stream order (after every step issued so far) and transferred to u_host on a second stream while
+ * the caller already issues the next ggp_step.  u_host (M pointers, as ggp_get_state) must stay valid -- and
+ * should be page-locked (ggp_host_alloc) for the transfer to be asynchronous -- until ggp_save_wait returns.
+ * A further ggp_save_async waits on the device for the previous transfer; ggp_save_wait blocks the host until
+ * every transfer issued so far has landed.
+ */
+int ggp_save_async(ggp_plan *plan, void *const *u_host);
+int ggp_save_wait(ggp_plan *plan);
+
+/*
+ * Checkpoint / resume (the reference has none).  The blob holds the fields plus the
+ * plan state that is not in the descriptor -- half-step counter (Philox counter word) and the pump amplitude
+ * of F_now (quirk Q1) -- so that  create(desc) + ggp_checkpoint_load + ggp_step(n2)  continues a run
+ * bit-identically to the uninterrupted  ggp_step(n1); ggp_step(n2).  Loading into a plan of another shape,
+ * precision or trajectory shard fails with GGP_ERR_INVALID.  The time t, the position in the pump schedule
+ * and ts stay with the caller (they are Julia-side state).
+ */
+int64_t ggp_checkpoint_bytes(ggp_plan *plan);
+int ggp_checkpoint_save(ggp_plan *plan, void *blob, uint64_t capacity);
+int ggp_checkpoint_load(ggp_plan *plan, const void *blob, uint64_t size);
+
 /* Ensemble observables summed over this plan's trajectories, written as doubles to out_host.
    If a communicator was attached with ggp_comm_init the sums are all-reduced over ranks (NCCL). */
 int ggp_observe(ggp_plan *plan, int kind, double *out_host);
