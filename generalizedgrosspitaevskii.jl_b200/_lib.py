@@ -9,12 +9,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggp.so")
 LIB_PATH = os.environ.get("GGP_LIBRARY", LIB_PATH)  # A/B measurements of kernel variants (tools/)
 
-GGP_ABI_VERSION = 2
+GGP_ABI_VERSION = 3
 GGP_C64, GGP_C128 = 0, 1
 TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL = 0, 1, 2, 3
 NL_NONE, NL_DIAG = 0, 1
 PUMP_NONE, PUMP_SEPARABLE = 0, 1
-NOISE_NONE, NOISE_CONST = 0, 1
+NOISE_NONE, NOISE_CONST, NOISE_FIELD = 0, 1, 2
 OBS_DENSITY, OBS_MOMENTUM, OBS_NORM = 0, 1, 2
 
 EXPORTS = [
@@ -46,6 +46,8 @@ class GgpDesc(C.Structure):
         ("noise_kind", C.c_int32), ("noise_real", C.c_int32),
         ("noise_eta", (C.c_double * 2) * 2), ("seed", C.c_uint64),
         ("slab_nranks", C.c_int32), ("slab_rank", C.c_int32),
+        ("noise_alpha", ((C.c_double * 2) * 2) * 2), ("noise_profile", C.c_void_p),
+        ("disp_sep_tol", C.c_double),
     ]
 
 

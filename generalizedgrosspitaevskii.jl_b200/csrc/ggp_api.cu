@@ -420,6 +420,7 @@ struct PlanT : PlanBase {
     // modes, 3e-10 at the populated ones); the factorised product stays inside the table's own rounding.
     // GGP_NO_SEP=1 disables the fast path, GGP_SEP_TOL overrides the tolerance.
     double tol = (d.table_precision == GGP_C128 && sizeof(T) == 8) ? 1e-13 : 4e-6;
+    if (d.disp_sep_tol > 0) tol = d.disp_sep_tol;  // the host verified in Float64 that D is a sum over axes (ggp.h)
     if (const char* e = getenv("GGP_SEP_TOL")) tol = atof(e);
     if (!(emax <= tol * dmax)) return 0;
     std::vector<cpx<T>> hp((size_t)np), hl((size_t)nl);
@@ -646,6 +647,23 @@ struct PlanT : PlanBase {
       pw.noise = NOISE_PHILOX;
       pw.noise_real = d.noise_real;
       for (int i = 0; i < M; ++i) pw.eta[i] = mk<T>((T)d.noise_eta[i][0], (T)d.noise_eta[i][1]);
+      if (noise_kind == GGP_NOISE_FIELD) {
+        pw.noise_field = 1;
+        pw.n1 = (int)n[0];
+        for (int i = 0; i < M; ++i)
+          for (int j = 0; j < M; ++j) pw.alpha[i][j] = mk<T>((T)d.noise_alpha[i][j][0], (T)d.noise_alpha[i][j][1]);
+        if (d.noise_profile) {
+          std::vector<cpx<T>> hp((size_t)n[0]);
+          const double* src = (const double*)d.noise_profile;
+          for (long long k = 0; k < n[0]; ++k) hp[(size_t)k] = mk<T>((T)src[2 * k], (T)src[2 * k + 1]);
+          cpx<T>* dp = nullptr;
+          if ((rc = dalloc((void**)&dp, sizeof(cpx<T>) * hp.size()))) return rc;
+          GGP_CUDA(cudaMemcpy(dp, hp.data(), sizeof(cpx<T>) * hp.size(), cudaMemcpyHostToDevice));
+          pw.nprof = dp;
+        }
+      } else if (noise_kind != GGP_NOISE_CONST) {
+        return fail(GGP_ERR_INVALID, "unknown noise_kind");
+      }
       pw.seed_lo = (uint32_t)d.seed;
       pw.seed_hi = (uint32_t)(d.seed >> 32);
       pw.elem_offset = batch_offset * nspatial;

@@ -16,6 +16,9 @@
 #include "tma.cuh"
 
 #define GGP_MAX_PEERS 8
+#ifndef GGP_STR_D2_BLOCKS
+#define GGP_STR_D2_BLOCKS 2
+#endif
 
 namespace ggp {
 
@@ -108,6 +111,9 @@ struct KCfg {
   // bounds ask for as many CTAs per SM as that allows; wider data (M = 2, long fp64 lines) takes what it needs
   __host__ __device__ static constexpr int data_regs(int M) { return M * E * (int)sizeof(cpx<T>) / 4; }
   __host__ __device__ static constexpr int str_min_blocks(int M) {
+    // two-component fp64 tiles (64 data registers, 256 threads): left alone the compiler takes 206 registers = ONE
+    // 8-warp CTA per SM (C3, ncu r01t: issue-active 11.5 %); capped at 128 two CTAs fit
+    if (sizeof(T) == 8 && data_regs(M) == 64 && STR_THREADS <= 256) return GGP_STR_D2_BLOCKS;
     return data_regs(M) <= 32 ? 1024 / STR_THREADS : 1;
   }
   // Tuning headroom: the fp32 kernels that fit 64 registers may be launched with twice the tile width (1024

@@ -41,6 +41,12 @@ struct PointwiseParams {
   int noise;   // NOISE_*
   int noise_real;
   cpx<T> eta[2];
+  // GGP_NOISE_FIELD: eta_i(u, r) = P[k1] (eta_i + sum_j alpha_ij |u_j|), |u_j| of the pre-update field; P indexed by
+  // the first grid index only (the reference's `point`, quirk Q2); nprof == nullptr: P = 1
+  int noise_field;
+  cpx<T> alpha[2][2];
+  const cpx<T>* nprof;
+  int n1;
   uint32_t seed_lo, seed_hi;
   long long elem_offset;  // global element index of this plan's element 0 (batch_offset * nspatial)
 };
@@ -171,6 +177,24 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
     }
     return;
   }
+  // field-dependent noise amplitude: |u_j| of the PRE-update field (src/kernels.jl:40-42)
+  cpx<T> etav[M];
+  if (PWV == PW_STOCH && p.noise) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) etav[i] = p.eta[i];
+    if (p.noise_field) {
+      T av[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) av[j] = sqrt(cabs2(f[j]));
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+          etav[i] = mk<T>(fma_(p.alpha[i][j].x, av[j], etav[i].x), fma_(p.alpha[i][j].y, av[j], etav[i].y));
+        if (p.nprof) etav[i] = cmul(p.nprof[sidx % p.n1], etav[i]);
+      }
+    }
+  }
   // nonlinear phase on the pre-update field, kept as ph = cis(-dt G) - 1
   cpx<T> ph[M];
   if (p.nl) {
@@ -240,7 +264,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
         xi = normal_from<T>(rnd[i], h.ctr, p.noise_real);
       }
       // -i sqrt(dt) eta xi
-      const cpx<T> ex = cmul(p.eta[i], xi);
+      const cpx<T> ex = cmul(etav[i], xi);
       res[i] = res[i] + mk<T>(p.sqrt_dt * ex.y, -p.sqrt_dt * ex.x);
     }
   }

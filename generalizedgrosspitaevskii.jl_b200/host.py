@@ -274,6 +274,50 @@ def exp_table(f, grid, param, dt, M):
     return kind, np.ascontiguousarray(table)
 
 
+def separable_dispersion_tol(f, grid, param, table, rng=None):
+    """`disp_sep_tol` of include/ggp.h for a scalar dispersion table of a ComplexF32 problem: if D(k) is a sum over
+    axes in Float64 arithmetic (checked on random grid points: the mixed second difference
+    D(k) - sum_a D(k_a e_a) + (d-1) D(0) vanishes), return the deviation of the given table from the product of its
+    own axis factors (its rounding, eps32 * |phase|) with a 25 % margin; otherwise 0 (library default)."""
+    d = len(grid)
+    if d < 2:
+        return 0.0
+    rng = rng or np.random.default_rng(0x5E9)
+    g64 = [np.asarray(g, dtype=np.float64) for g in grid]
+    idx = [rng.integers(0, len(g), size=2048) for g in g64]
+    zero = [np.full(2048, g[0]) for g in g64]           # k = 0 is the first entry of every fftfreq axis
+    pts = [g[i] for g, i in zip(g64, idx)]
+
+    def D(p):
+        v = f(tuple(p), param)
+        if isinstance(v, (SVector, SMatrix)):
+            return None
+        return np.asarray(v, dtype=np.complex128) + np.zeros(2048)
+
+    full, origin = D(pts), D(zero)
+    if full is None or origin is None:
+        return 0.0
+    acc = full + (d - 1) * origin
+    for a in range(d):
+        acc = acc - D([pts[b] if b == a else zero[b] for b in range(d)])
+    scale = max(1e-300, float(np.abs(full).max()))
+    if float(np.abs(acc).max()) > 1e-12 * scale:
+        return 0.0
+    # deviation of the table from perp (x) line, where line runs along the LAST axis (the strided kernel's)
+    shape = tuple(len(g) for g in reversed(grid))           # (n_d, ..., n_1)
+    tab = np.asarray(table).reshape(shape[0], -1)
+    d0 = tab[0, 0]
+    if d0 == 0 or not np.isfinite(d0):
+        return 0.0
+    line, perp = tab[:, 0] / d0, tab[0, :]
+    dev, dmax = 0.0, 0.0
+    for l0 in range(0, shape[0], 256):                      # chunked: the table may be hundreds of MB
+        blk = tab[l0:l0 + 256]
+        dev = max(dev, float(np.abs(blk - line[l0:l0 + 256, None] * perp[None, :]).max()))
+        dmax = max(dmax, float(np.abs(blk).max()))
+    return 1.25 * dev / dmax + 1e-9 if dmax > 0 else 0.0
+
+
 # ------------------------------------------------------------------------------------------------
 # closure recognition (registered forms, SURVEY §8a)
 # ------------------------------------------------------------------------------------------------
@@ -393,28 +437,88 @@ class PumpModel:
         return complex(np.asarray(val, dtype=complex).reshape(())) / complex(self._ref)
 
 
+def noise_points(grid):
+    """The `point`s the reference hands to the noise amplitude function: every grid axis indexed with the FIRST
+    index K[1] (src/kernels.jl:27,41).  Returns an (n1, d) array, or None where Julia would throw a
+    BoundsError (n1 longer than another axis)."""
+    n1 = len(grid[0])
+    if any(len(g) < n1 for g in grid):
+        return None
+    return np.stack([np.asarray(g[:n1]) for g in grid], axis=1)
+
+
 def recognise_noise(f, prob, rng=None):
-    """eta_i = const per component (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29)."""
+    """Registered form  eta_i(u, r) = P(r) (e_i + sum_j a_ij |u_j|):  constant amplitudes
+    (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29, SVector docs/src/stochastic_simulations.md:80-86),
+    field-dependent `alpha*abs(u[1])` (:68-72) and spatial profiles (:74-78).
+    Returns (e[M], a[M][M], P) -- P is None (no position dependence) or the n1 values of the profile at the
+    reference's Q2 points, normalised to 1 at the probe point."""
     rng = rng or np.random.default_rng(0xBEEF)
     M = len(prob.u0)
     grid = direct_grid(prob)
-    vals = []
-    for _ in range(4):
-        u = SVector([complex(rng.standard_normal(), rng.standard_normal()) for _ in range(M)])
-        r = tuple(g[rng.integers(len(g))] for g in grid)
-        v = f(u, r, prob.param)
+    pts = noise_points(grid)
+
+    def evaluate(u, r):
+        v = f(SVector([u[j] for j in range(M)]), r, prob.param)
+        if isinstance(v, SMatrix):
+            raise UnsupportedForm("matrix-valued noise amplitudes are not a registered form")
         if isinstance(v, SVector):
-            v = [complex(np.asarray(x).reshape(())) for x in v]
             if len(v) != M:
                 raise UnsupportedForm("noise amplitude SVector must have length M")
-        else:
-            v = [complex(np.asarray(v).reshape(()))] * M
-        vals.append(v)
-    vals = np.array(vals)
-    if np.abs(vals - vals[0]).max() > 1e-12 * max(1e-300, np.abs(vals).max()):
-        raise UnsupportedForm("field- or position-dependent noise amplitudes are not a registered form yet "
-                              "(SURVEY §8f N4); the B200 backend has no CPU fallback")
-    return vals[0]
+            return np.array([complex(np.asarray(x).reshape(())) for x in v])
+        return np.full(M, complex(np.asarray(v).reshape(())))
+
+    def probe():
+        return rng.uniform(0.2, 2.0, size=M) * np.exp(2j * np.pi * rng.uniform(size=M))
+
+    r_mid = tuple(g[len(g) // 2] for g in grid) if pts is None else tuple(pts[len(pts) // 2])
+    # reference point: where the amplitude is largest along the Q2 points (a profile may vanish somewhere)
+    u_ref = probe()
+    k0 = None
+    if pts is not None:
+        along = np.array([evaluate(u_ref, tuple(pts[k])) for k in range(len(pts))])         # (n1, M)
+        k0 = int(np.abs(along).max(axis=1).argmax())
+        r0 = tuple(pts[k0])
+    else:
+        r0 = r_mid
+    # field dependence at r0:  least squares on the features (1, |u_1|, ..., |u_M|), checked on held-out probes
+    P_ = 4 * (M + 1) + 8
+    U = [probe() for _ in range(P_)]
+    A = np.array([[1.0] + list(np.abs(u)) for u in U])
+    Y = np.array([evaluate(u, r0) for u in U])                                                # (P_, M)
+    coef, *_ = np.linalg.lstsq(A, Y, rcond=None)                                              # (M+1, M)
+    V = [probe() for _ in range(12)]
+    pred = np.array([[1.0] + list(np.abs(u)) for u in V]) @ coef
+    truth = np.array([evaluate(u, r0) for u in V])
+    scale = max(1e-300, np.abs(truth).max(), np.abs(coef).max())
+    if np.abs(pred - truth).max() > 1e-9 * scale:
+        raise UnsupportedForm("noise amplitude is not of the registered form P(r) (e_i + sum_j a_ij |u_j|); "
+                              "the B200 backend has no CPU fallback")
+    coef[np.abs(coef) < 1e-13 * scale] = 0
+    e, a = coef[0].copy(), coef[1:].T.copy()                                                  # a[i][j]
+    # position dependence
+    profile = None
+    if pts is None:
+        # Julia would index out of bounds as soon as the closure is called; closures that ignore r are fine
+        other = evaluate(u_ref, tuple(g[0] for g in grid))
+        if np.abs(other - evaluate(u_ref, r0)).max() > 1e-12 * scale:
+            raise UnsupportedForm("position-dependent noise with n1 longer than another axis: the reference's "
+                                  "`point` (src/kernels.jl:27,41) is out of bounds there")
+    else:
+        ref = evaluate(u_ref, r0)
+        c = int(np.abs(ref).argmax())
+        if abs(ref[c]) > 0:
+            prof = along[:, c] / ref[c]
+            if np.abs(prof - 1).max() > 1e-12:
+                u2 = probe()
+                base = evaluate(u2, r0)
+                for k in (0, len(pts) // 3, len(pts) - 1):
+                    if np.abs(evaluate(u2, tuple(pts[k])) - prof[k] * base).max() > 1e-9 * scale:
+                        raise UnsupportedForm("noise amplitude does not separate as P(r) x (field part)")
+                if np.abs(along - prof[:, None] * ref[None, :]).max() > 1e-9 * scale:
+                    raise UnsupportedForm("noise amplitude profile differs between components")
+                profile = np.ascontiguousarray(prof, dtype=np.complex128)
+    return e, a, profile
 
 
 # ------------------------------------------------------------------------------------------------
@@ -520,6 +624,8 @@ class StrangSplittingIterator:
             return a.ctypes.data
 
         d.disp_kind, d.pot_kind = dkind, vkind
+        if dkind == L.TABLE_SCALAR and dtype == np.complex64 and slab is None and not os.environ.get("GGP_NO_SEP_HINT"):
+            d.disp_sep_tol = separable_dispersion_tol(prob.dispersion, rg, prob.param, dtab)
         d.disp_table = as_c128(dtab) if dtab is not None else None
         d.pot_table = as_c128(vtab) if vtab is not None else None
 
@@ -559,12 +665,20 @@ class StrangSplittingIterator:
         if not _absent(prob.position_noise_func):
             if _absent(prob.noise_prototype):
                 raise ValueError("position_noise_func needs a noise_prototype")
-            eta = recognise_noise(prob.position_noise_func, prob)
+            eta, alpha, profile = recognise_noise(prob.position_noise_func, prob)
             proto = prob.noise_prototype[0]
             self.noise_real = not np.iscomplexobj(proto)
-            d.noise_kind, d.noise_real = L.NOISE_CONST, int(self.noise_real)
+            field = bool(np.any(alpha != 0)) or profile is not None
+            if field and slab is not None:
+                raise UnsupportedForm("field-/position-dependent noise with a slab decomposition")
+            d.noise_kind, d.noise_real = (L.NOISE_FIELD if field else L.NOISE_CONST), int(self.noise_real)
             for i in range(M):
                 d.noise_eta[i][0], d.noise_eta[i][1] = eta[i].real, eta[i].imag
+                for j in range(M):
+                    d.noise_alpha[i][j][0], d.noise_alpha[i][j][1] = alpha[i, j].real, alpha[i, j].imag
+            if profile is not None:
+                d.noise_profile = as_c128(profile)
+            self.noise_form = (eta, alpha, profile)
             if rng is None:
                 seed = int.from_bytes(os.urandom(8), "little")
             elif isinstance(rng, (int, np.integer)):

@@ -6,7 +6,7 @@
 # mirror (../host.py) implements the same logic line for line and IS exercised by the test-suite.
 using Libdl
 
-const GGP_ABI_VERSION = UInt32(2)
+const GGP_ABI_VERSION = UInt32(3)
 const GGP_C64, GGP_C128 = Int32(0), Int32(1)
 const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL = Int32(0), Int32(1), Int32(2), Int32(3)
 
@@ -44,6 +44,9 @@ struct GgpDesc
     seed::UInt64
     slab_nranks::Int32           # 3-D slab decomposition (0/1 = off), see include/ggp.h
     slab_rank::Int32
+    noise_alpha::NTuple{8,Float64}   # GGP_NOISE_FIELD: alpha_ij [i][j][re/im]
+    noise_profile::Ptr{Cvoid}        # GGP_NOISE_FIELD: n[1] ComplexF64 values P(point(k1)) or C_NULL (quirk Q2)
+    disp_sep_tol::Float64            # 0 = library default; see include/ggp.h (separable dispersion)
 end
 
 const _lib = Ref{Ptr{Cvoid}}(C_NULL)

@@ -74,17 +74,76 @@ function recognise_pump(pump, prob, tspan, times)
     S, ncomp, amp
 end
 
-"η_i = const per component"
+"""
+Registered noise form  η_i(u, r) = P(r)·(e_i + Σ_j a_ij |u_j|)  (host.py: recognise_noise): constant amplitudes,
+`α·abs(u[1])` and spatial profiles of docs/src/stochastic_simulations.md:62-86.  Returns `(e, a, P)`; `P` is
+`nothing` or the n₁ profile values at the reference's points `(x[k], y[k], …)` — `build_field_at(grid, K)` indexes every
+grid axis with `K[1]` (src/kernels.jl:27,41; quirk Q2).
+"""
 function recognise_noise(f, prob)
     M = length(prob.u0)
     rng = Random.Xoshiro(0xBEEF)
     rs = direct_grid(prob)
-    vals = map(1:4) do _
-        u = SVector{M,ComplexF64}(ntuple(_ -> randn(rng, ComplexF64), M))
-        r = map(g -> g[rand(rng, 1:length(g))], rs)
-        collect(_aslist(f(u, r, prob.param), M)[1])
+    n1 = length(rs[1])
+    inbounds = all(g -> length(g) ≥ n1, rs)
+    pts = inbounds ? [map(g -> g[k], rs) for k in 1:n1] : nothing
+    ev(u, r) = ComplexF64.(collect(_aslist(f(SVector{M,ComplexF64}(u), r, prob.param), M)[1]))
+    probe() = ntuple(_ -> (0.2 + 1.8rand(rng)) * cis(2π * rand(rng)), M)
+    uref = probe()
+    along = pts === nothing ? nothing : [ev(uref, r) for r in pts]
+    k0 = along === nothing ? 0 : argmax(map(v -> maximum(abs, v), along))
+    r0 = along === nothing ? map(g -> g[cld(length(g), 2)], rs) : pts[k0]
+    U = [probe() for _ in 1:(4(M + 1) + 8)]
+    A = [j == 0 ? 1.0 : abs(u[j]) for u in U, j in 0:M]
+    Y = permutedims(reduce(hcat, [ev(u, r0) for u in U]))
+    coef = A \ Y                                                  # (M+1) × M
+    V = [probe() for _ in 1:12]
+    pred = [j == 0 ? 1.0 : abs(u[j]) for u in V, j in 0:M] * coef
+    truth = permutedims(reduce(hcat, [ev(u, r0) for u in V]))
+    scale = max(maximum(abs, truth), maximum(abs, coef), floatmin(Float64))
+    maximum(abs, pred .- truth) ≤ 1e-9scale ||
+        error("noise amplitude is not of the registered form P(r)·(e_i + Σ_j a_ij |u_j|) (no CPU fallback)")
+    coef[abs.(coef) .< 1e-13scale] .= 0
+    e, a = coef[1, :], permutedims(coef[2:end, :])                 # a[i, j]
+    P = nothing
+    if pts === nothing
+        maximum(abs, ev(uref, map(first, rs)) .- ev(uref, r0)) ≤ 1e-12scale ||
+            error("position-dependent noise with n₁ longer than another axis: the reference's `point` is out of bounds")
+    else
+        ref = along[k0]; c = argmax(abs.(ref))
+        if abs(ref[c]) > 0
+            prof = ComplexF64[v[c] / ref[c] for v in along]
+            if maximum(abs, prof .- 1) > 1e-12
+                all(k -> maximum(abs, along[k] .- prof[k] .* ref) ≤ 1e-9scale, 1:n1) ||
+                    error("noise amplitude does not separate as P(r) × (field part)")
+                P = prof
+            end
+        end
     end
-    all(v -> maximum(abs, v .- vals[1]) ≤ 1e-12 * max(maximum(abs, vals[1]), floatmin(Float64)), vals) ||
-        error("field- or position-dependent noise amplitudes are not a registered form yet (no CPU fallback)")
-    vals[1]
+    e, a, P
+end
+
+"""
+`disp_sep_tol` of include/ggp.h (host.py: separable_dispersion_tol): for a ComplexF32 problem whose scalar dispersion
+is a sum over axes in Float64 arithmetic, the deviation of the table from the product of its own axis factors (its
+rounding, eps32·|phase|) with a 25 % margin; otherwise 0 (library default).
+"""
+function separable_dispersion_tol(D, rg, param, table::AbstractArray{<:Number})
+    d = length(rg); d < 2 && return 0.0
+    rng = Random.Xoshiro(0x5E9)
+    g = map(x -> Float64.(collect(x)), rg)
+    for _ in 1:2048
+        k = map(x -> x[rand(rng, 1:length(x))], g)
+        z = map(x -> x[1], g)
+        full = D(k, param); full isa Number || return 0.0
+        acc = ComplexF64(full) + (d - 1) * ComplexF64(D(z, param))
+        for a in 1:d
+            acc -= ComplexF64(D(ntuple(b -> b == a ? k[b] : z[b], d), param))
+        end
+        abs(acc) ≤ 1e-12 * max(abs(full), floatmin(Float64)) || return 0.0
+    end
+    tab = reshape(ComplexF64.(table), :, size(table, d))          # (perp, line): the strided kernel runs along the last axis
+    d0 = tab[1, 1]; (d0 == 0 || !isfinite(d0)) && return 0.0
+    dev = maximum(abs, tab .- tab[:, 1] .* permutedims(tab[1, :]) ./ d0)
+    1.25dev / maximum(abs, tab) + 1e-9
 end

@@ -55,6 +55,10 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
     dkind = (M == 1 && _kind(exp_D) != GGP_TABLE_NONE) ? GGP_TABLE_SCALAR : _kind(exp_D)
     vkind = (M == 1 && _kind(exp_V) != GGP_TABLE_NONE) ? GGP_TABLE_SCALAR : _kind(exp_V)
 
+    # ComplexF32 problems: keep the separable-dispersion fast path on large grids (include/ggp.h: disp_sep_tol)
+    sep_tol = (CT == ComplexF32 && dkind == GGP_TABLE_SCALAR && exp_D isa AbstractArray{<:Number}) ?
+              separable_dispersion_tol(prob.dispersion, rg, prob.param, exp_D) : 0.0
+
     nl_kind = Int32(0); nl_scalar = Int32(0); nl_c = ntuple(_ -> 0.0, 4); nl_g = ntuple(_ -> 0.0, 8)
     if !(prob.nonlinearity isa AdditiveIdentity)
         sc, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, Val(M))
@@ -82,9 +86,16 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
     end
 
     noise_kind = Int32(0); noise_real = Int32(0); eta = ntuple(_ -> 0.0, 4); seed = UInt64(0)
+    alpha = ntuple(_ -> 0.0, 8); nprof = ComplexF64[]
     if !(prob.position_noise_func isa AdditiveIdentity)
-        e = recognise_noise(prob.position_noise_func, prob)
-        noise_kind = Int32(1); noise_real = Int32(eltype(first(prob.noise_prototype)) <: Real)
+        e, al, P = recognise_noise(prob.position_noise_func, prob)
+        field = any(!iszero, al) || P !== nothing
+        noise_kind = Int32(field ? 2 : 1); noise_real = Int32(eltype(first(prob.noise_prototype)) <: Real)
+        alpha = ntuple(k -> begin
+                i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
+                (i > M || j > M) ? 0.0 : (isodd(k) ? real(al[i, j]) : imag(al[i, j]))
+            end, 8)
+        P === nothing || (nprof = P)
         eta = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(e[i]) : imag(e[i]))), 4)
         seed = rng === nothing ? rand(UInt64) : rand(rng, UInt64)
     end
@@ -93,8 +104,9 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
         ntuple(i -> i ≤ N ? Int64(sz[i]) : Int64(1), 3), Int64(nbatch), Int64(batch_offset),
         CT == ComplexF32 ? GGP_C64 : GGP_C128, GGP_C128, Int32(device), Int32(0), C_NULL, Float64(dt),
         dkind, vkind, _ptr(dflat), _ptr(vflat), nl_kind, nl_scalar, nl_c, nl_g,
-        pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed, Int32(0), Int32(0))
-    handle = GC.@preserve dflat vflat sflat ggp_plan_create(desc)
+        pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed, Int32(0), Int32(0),
+        alpha, _ptr(nprof), sep_tol)
+    handle = GC.@preserve dflat vflat sflat nprof ggp_plan_create(desc)
     ggp_set_state(handle, host_u0)                                                    # u = copy.(prob.u0), :48
 
     iter = StrangSplittingIterator(prob, dt, ts, steps_per_save, save_start, _progress, progress, result,

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGP_ABI_VERSION 2u
+#define GGP_ABI_VERSION 3u
 
 typedef enum ggp_status {
   GGP_OK = 0,
@@ -74,7 +74,9 @@ typedef enum ggp_pump_kind {
 
 typedef enum ggp_noise_kind {
   GGP_NOISE_NONE = 0,
-  GGP_NOISE_CONST = 1 /* eta_i(u,r) = const (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29) */
+  GGP_NOISE_CONST = 1, /* eta_i(u,r) = const (examples/truncated_wigner.jl:96, test/windowed_ft.jl:27-29) */
+  GGP_NOISE_FIELD = 2  /* eta_i(u,r) = P(r) * (eta_i + sum_j alpha_ij |u_j|): field-dependent and spatially varying
+                          amplitudes of docs/src/stochastic_simulations.md:68-79 */
 } ggp_noise_kind;
 
 typedef enum ggp_observable {
@@ -135,6 +137,23 @@ typedef struct ggp_desc {
      all-to-all transpose, in which the z lines are local).  Needs ggp_comm_init before ggp_step. */
   int32_t slab_nranks;
   int32_t slab_rank;
+
+  /* GGP_NOISE_FIELD only (ABI 3).  noise_alpha: coefficients of |u_j| (evaluated on the PRE-update field like
+     G, src/kernels.jl:40-42).  noise_profile: NULL, or n[0] complex doubles P(point(k1)), k1 = 0..n[0]-1 -- the
+     reference builds `point` by indexing EVERY grid axis with the first index K[1] (src/kernels.jl:27,41; SURVEY
+     quirk Q2), so the spatial profile it applies is a function of the first (fastest) index only. */
+  double noise_alpha[2][2][2]; /* alpha_ij [i][j][re/im] */
+  const void *noise_profile;
+
+  /* Separable dispersion (ABI 3).  A scalar exp_D that factorises as Dperp(k_1..k_{d-1}) * Dline(k_d) -- any
+     dispersion that is a sum over axes, e.g. |k|^2/2 -- is held as those two factors and the full table is never
+     read by the kernels.  The library checks the factorisation numerically on disp_table and accepts it if the
+     largest deviation is <= tol * max|exp_D|, tol = 1e-13 (ComplexF64 plans) or 4e-6 (ComplexF32 plans).  A
+     ComplexF32 problem's table is cis(-dt * fl32(D(k))): it deviates from ANY product by its own rounding,
+     eps32 * |phase|, which exceeds 4e-6 on large grids (4096^2 with L = 64: 5e-6).  A host that has verified in
+     Float64 that the dispersion is a sum over axes passes the measured deviation here so that the fast path is
+     kept; 0 = library default. */
+  double disp_sep_tol;
 } ggp_desc;
 
 typedef struct ggp_plan ggp_plan;

@@ -309,6 +309,22 @@ def _mesh(axes):
     return tuple(out)
 
 
+def _noise_points(axes):
+    """The `point` the reference hands to the noise amplitude function (kernels.jl:41): build_field_at(grid, K)
+    indexes EVERY 1-D grid axis with K[1] (`_getindex(A, K) = A[K[1:ndims(A)]...]`, kernels.jl:27) -- quirk Q2:
+    point = (x[K1], y[K1], ...), a function of the first (fastest) index only; a BoundsError in Julia if n1 exceeds
+    the length of another axis (IndexError here).  Identical to the true mesh in 1-D."""
+    d = len(axes)
+    n1 = len(axes[0])
+    out = []
+    for ax in axes:
+        if len(ax) < n1:
+            raise IndexError("BoundsError: noise `point` indexes every grid axis with K[1] (src/kernels.jl:27,41) "
+                             "and n1 exceeds the length of another axis")
+        out.append(np.asarray(ax[:n1]).reshape([1] * (d - 1) + [n1]))
+    return tuple(out)
+
+
 # --------------------------------------------------------------------------------------------
 # problem container -- problem.jl:97-122
 # --------------------------------------------------------------------------------------------
@@ -455,6 +471,28 @@ class StrangSplitting:
     pass
 
 
+class _LazyNoisePoints:
+    """Q2 points, built on first element access: closures that ignore `r` (every shipped one) never trigger the
+    reference's out-of-bounds case for n1 > n2."""
+
+    def __init__(self, axes):
+        self.axes, self._pts = axes, None
+
+    def _get(self):
+        if self._pts is None:
+            self._pts = _noise_points(self.axes)
+        return self._pts
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return len(self.axes)
+
+
 class StrangSplittingIterator:
     def __init__(self, prob, tspan, *, dt, nsaves, save_start=True, noise_source=None,
                  record_noise=None, fft_workers=None):
@@ -483,6 +521,7 @@ class StrangSplittingIterator:
         self.result = [np.stack([x] * (nsaves + self.save_start), axis=0) for x in prob.u0]  # :41-43
         self._point_direct = _mesh(self.dg)
         self._point_recip = _mesh(self.rg)
+        self._point_noise = None if _is_add_id(prob.position_noise_func) else _LazyNoisePoints(self.dg)
 
     # misc.jl:44-51
     def _sample_noise(self):
@@ -507,7 +546,8 @@ class StrangSplittingIterator:
             self.pump_now = self.pump_next
             self.pump_next = evaluate_pump(prob, t)
         self.u = muladd(self.u, self.exp_Vdt, self.pump_next, self.pump_now, dt, prob.nonlinearity,
-                        prob.position_noise_func, xi, prob.param, self._point_direct)        # :82-83
+                        prob.position_noise_func, xi, prob.param,
+                        self._point_noise if self._point_noise is not None else self._point_direct)  # :82-83 (Q2)
 
     # strang_splitting.jl:69-76
     def diffusion_step(self):

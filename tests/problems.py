@@ -265,3 +265,44 @@ def kerr3d_slab(ns, N=512, rank=0, world=1, dtype=np.complex64, L=32.0, g=1.0, d
     return dict(u0=(u0,), lengths=(Lr, Lr, Lr),
                 kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=SimpleNamespace(g=real(g))),
                 tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=1)
+
+
+def noise_forms(ns, form="field", ndim=1, M=1, N=32, ntraj=3, dtype=np.complex128, real_proto=False):
+    """Noise amplitudes of docs/src/stochastic_simulations.md:62-86 beyond the constant one:
+    `field`  alpha*abs(u[1]) + const,  `profile`  beta*exp(-sum(abs2, r)/sigma2),  `both`  profile x (const + |u|)
+    with an SVector return for M = 2.  Damped free dispersion + Kerr term so that every stage of the half-step runs."""
+    L = 10.0
+    rng = np.random.default_rng(42)
+    shape = (ntraj,) + (N,) * ndim
+    u0 = tuple(((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / 2).astype(dtype) for _ in range(M))
+    param = SimpleNamespace(alpha=0.3, beta=0.7, sigma2=30.0, c=0.2, g=0.5, gamma=0.1)
+
+    def dispersion(ks, p):
+        return _sumsq(ks) / 2 - 1j * p.gamma / 2
+
+    def nonlinearity(u, p):
+        return p.g * ns.abs2(u[0])
+
+    def prof(r, p):
+        s = 0
+        for ri in r:
+            s = s + ri * ri
+        return p.beta * np.exp(-s / p.sigma2)
+
+    if form == "field":
+        def eta(u, r, p):
+            return p.c + p.alpha * abs(u[0])
+    elif form == "profile":
+        def eta(u, r, p):
+            return prof(r, p)
+    else:
+        def eta(u, r, p):
+            if M == 1:
+                return prof(r, p) * (p.c + p.alpha * abs(u[0]))
+            return ns.SVector(prof(r, p) * (p.c + p.alpha * abs(u[1])), prof(r, p) * (2 * p.c + 0.5 * p.alpha * abs(u[0])))
+    real_t = np.float32 if dtype == np.complex64 else np.float64
+    proto = tuple(np.empty(x.shape, dtype=real_t if real_proto else dtype) for x in u0)
+    return dict(u0=u0, lengths=(L,) * ndim,
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=param,
+                            noise_prototype=proto, position_noise_func=eta),
+                tspan=(0, 0.5), dt=0.05, nsaves=2, save_start=True)

@@ -156,6 +156,26 @@ def test_truncated_wigner_host_noise_2d(G):
     assert rel_l2(g, o) <= 1e-10
 
 
+@pytest.mark.parametrize("form,ndim,M,dtype,real_proto", [
+    ("field", 1, 1, np.complex128, False),
+    ("profile", 1, 1, np.complex128, False),
+    ("both", 1, 1, np.complex64, False),
+    ("both", 2, 2, np.complex128, False),      # SVector amplitudes, profile at the reference's Q2 points (x[K1], y[K1])
+    ("field", 2, 1, np.complex128, True),      # real noise prototype
+])
+def test_field_and_position_dependent_noise_host_fed(G, form, ndim, M, dtype, real_proto):
+    """eta_i(u, r) = P(r) (e_i + sum_j a_ij |u_j|) (docs/src/stochastic_simulations.md:62-86) against the
+    oracle, which calls the user's closure with the reference's own `point` (src/kernels.jl:27,41), on identical
+    host-fed noise."""
+    g, o = run_both(G, P.noise_forms, noise_seed=11, form=form, ndim=ndim, M=M, dtype=dtype, real_proto=real_proto)
+    assert rel_l2(g, o) <= TOL[np.dtype(dtype)]
+    # the noise really depends on the field / position: switching the form off changes the answer
+    g0, _ = run_both(G, P.noise_forms, noise_seed=11, form="field", ndim=ndim, M=M, dtype=dtype, real_proto=real_proto) \
+        if form != "field" else (None, None)
+    if g0 is not None:
+        assert rel_l2(g, g0) > 1e-3
+
+
 def test_windowed_ft_philox_known_answer(G):
     """test/windowed_ft.jl:92-99 with the in-kernel Philox stream (rtol 7e-2 at 10^4 trajectories)."""
     from test_oracle_known_answers import analytic_commutation, windowed_correlation

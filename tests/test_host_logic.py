@@ -138,13 +138,33 @@ def test_closure_recognition(G):
     prob_bad = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], dispersion=prob.dispersion, pump=bad)
     with pytest.raises(G.UnsupportedForm):
         host.PumpModel(bad, prob_bad, (0.0, 10.0), times)
-    # noise: constant scalar ok, field dependent rejected
+    # noise: eta_i(u, r) = P(r) (e_i + sum_j a_ij |u_j|)  (docs/src/stochastic_simulations.md:62-86)
     pbw = P.windowed_ft(G, ntraj=4)
     probw = G.GrossPitaevskiiProblem(pbw["u0"], pbw["lengths"], **pbw["kwargs"])
-    eta = host.recognise_noise(probw.position_noise_func, probw)
-    assert np.isclose(eta[0], np.sqrt(probw.param.gamma / 2 / probw.param.dL))
+    eta, alpha, prof = host.recognise_noise(probw.position_noise_func, probw)
+    assert np.isclose(eta[0], np.sqrt(probw.param.gamma / 2 / probw.param.dL)) and not alpha.any() and prof is None
+    eta, alpha, prof = host.recognise_noise(lambda u, r, p: 0.3 * abs(u[0]), probw)        # field-dependent (:68-72)
+    assert abs(eta[0]) < 1e-12 and np.isclose(alpha[0, 0], 0.3) and prof is None
+    eta, alpha, prof = host.recognise_noise(lambda u, r, p: 0.7 * np.exp(-sum(x * x for x in r) / 9.0), probw)  # (:74-78)
+    xs = np.asarray(G.direct_grid(probw)[0])
+    assert prof is not None and np.allclose(eta[0] * prof, 0.7 * np.exp(-xs ** 2 / 9.0), rtol=1e-12) and not alpha.any()
     with pytest.raises(G.UnsupportedForm):
-        host.recognise_noise(lambda u, r, p: abs(u[0]), probw)
+        host.recognise_noise(lambda u, r, p: abs(u[0]) ** 2, probw)                         # not linear in |u|
+    with pytest.raises(G.UnsupportedForm):
+        host.recognise_noise(lambda u, r, p: np.exp(-r[0] ** 2 * abs(u[0])), probw)         # does not separate
+    # >= 2-D: the reference's `point` is (x[K1], y[K1]) (quirk Q2): profile along the first index only; out of
+    # bounds -- rejected -- when n1 exceeds another axis, unless the closure ignores r
+    u2 = (np.zeros((8, 32), complex),)
+    prob2 = G.GrossPitaevskiiProblem(u2, (10.0, 10.0), position_noise_func=lambda u, r, p: 0.5,
+                                     noise_prototype=u2)
+    assert host.recognise_noise(prob2.position_noise_func, prob2)[2] is None
+    with pytest.raises(G.UnsupportedForm):
+        host.recognise_noise(lambda u, r, p: np.exp(-r[0] ** 2 - r[1] ** 2), prob2)
+    u3 = (np.zeros((32, 16), complex), np.zeros((32, 16), complex))
+    prob3 = G.GrossPitaevskiiProblem(u3, (8.0, 8.0), noise_prototype=u3,
+                                     position_noise_func=lambda u, r, p: G.SVector(1.0, 2.0 + 0.5 * abs(u[0])))
+    eta, alpha, prof = host.recognise_noise(prob3.position_noise_func, prob3)
+    assert np.allclose(eta, [1.0, 2.0]) and np.allclose(alpha, [[0, 0], [0.5, 0]]) and prof is None
 
 
 def test_pump_schedule_matches_oracle_times(G):

@@ -208,3 +208,23 @@ def test_pump_times_quirk_q1():
     """pump evaluated at t0, then t_{n+1}+dt/2 and t_{n+1}+dt (one dt late)."""
     t0, tt = O.pump_times((0, 1), 0.25, 1)
     assert t0 == 0 and np.allclose(tt, [[0.375, 0.5], [0.625, 0.75], [0.875, 1.0], [1.125, 1.25]])
+
+
+def test_noise_point_quirk_q2():
+    """kernels.jl:27,41: the `point` handed to the noise amplitude function indexes EVERY grid axis with K[1]."""
+    xs, ys = np.arange(4) * 0.5, np.arange(6) * 0.25
+    px, py = O._noise_points((xs, ys))
+    assert px.shape == (1, 4) and py.shape == (1, 4)
+    assert np.array_equal(px.ravel(), xs) and np.array_equal(py.ravel(), ys[:4])      # y[K1], not y[K2]
+    with pytest.raises(IndexError):
+        O._noise_points((ys, xs))                                                     # n1 = 6 > n2 = 4: BoundsError
+    import problems as P
+    pb = P.noise_forms(O, form="profile", ndim=2, M=1, N=8, ntraj=2)
+    prob = O.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    seen = []
+    inner = prob.position_noise_func
+    prob.position_noise_func = lambda u, r, p: (seen.append([np.asarray(x).shape for x in r]), inner(u, r, p))[1]
+    rng = np.random.default_rng(0)
+    src = lambda shape, dtype: (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dtype)
+    O.solve(prob, O.StrangSplitting(), (0, 0.1), dt=0.05, nsaves=1, noise_source=src)
+    assert seen and all(s == [(1, 8), (1, 8)] for s in seen)
