@@ -482,15 +482,16 @@ def main():
             it4.close()
         except Exception as e:  # extras must never take the headline down
             extra["c4_ensemble"] = dict(error=repr(e))
-        if world > 1:
+        if True:    # N = 1: the unsharded 512^3 grid, the reference point of the slab scaling
             try:
                 k5 = 20
                 r5 = measure(G, "c5", k5, 3, local, n=512, slab=(rank, world), do_e2e=False, do_flush=False,
-                             comm=lambda it: attach_comm(G, it, world, rank))
+                             comm=(lambda it: attach_comm(G, it, world, rank)) if world > 1 else None)
                 ms5 = allmax(r5["chained_ms"])
                 pts5 = allsum(float(r5["meta"]["points"]))
                 extra["c5_slab"] = dict(workload=r5["meta"]["workload"], scaling="strong", value=pts5 * k5 / (ms5 * 1e-3),
                                         unit=METRIC, ms_per_step=ms5 / k5, steps=k5,
+                                        frac_of_hbm_roofline_contract=88 * pts5 / world / (ms5 / k5 * 1e-3) / 1e9 / peak,
                                         per_kernel_ms=dict(row=r5["prof"]["ms"][0] / max(1, r5["prof"]["n"][0]),
                                                            str_d=r5["prof"]["ms"][1] / max(1, r5["prof"]["n"][1]),
                                                            str_fi=r5["prof"]["ms"][2] / max(1, r5["prof"]["n"][2])))

@@ -96,12 +96,12 @@ static int dispatch_str_tma(int N, int M, const StrTmaParams<T>& p, long long nf
 }
 #endif
 template <typename T>
-static void dispatch_str_query(int N, int M, long long nfast, int* W, int* LS, int* threads, int* us) {
+static void dispatch_str_query(int N, int M, int ax, long long nfast, int* W, int* LS, int* threads, int* us) {
   *W = 0;
   switch (N) {
 #define X(n)                                   \
   case n:                                      \
-    str_query<T, n>(M, nfast, W, LS, threads, us); \
+    str_query<T, n>(M, ax, nfast, W, LS, threads, us); \
     return;
     GGP_SIZES(X)
 #undef X
@@ -705,7 +705,7 @@ struct PlanT : PlanBase {
     }
     for (int ax = 1; ax < ndim; ++ax) {
       int W = 0, LS = 0, threads = 0, us = 0;
-      dispatch_str_query<T>((int)n[ax], M, n[0], &W, &LS, &threads, &us);
+      dispatch_str_query<T>((int)n[ax], M, ax, n[0], &W, &LS, &threads, &us);
       if (!W || !us) continue;
       const size_t esz = sizeof(cpx<T>);
       if ((size_t)W * esz < 16 || (n[0] * esz) % 16 != 0) continue;
@@ -936,6 +936,7 @@ struct PlanT : PlanBase {
       p.dkind = KIND_SEP;
     }
     p.mode = mode;
+    p.ax = ax;
     long long nother;
     if (ax == 1) {
       p.ls = g0;

@@ -83,17 +83,26 @@ int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
 }
 
 template <typename T, int N>
-void str_query(int M, long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
+void str_query(int M, int ax, long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
   using K = KCfg<T, N>;
   const int wmax = K::str_max_threads(M) / K::TPL;
   int W = K::WDEF;
   // opt-in: one 1024-thread CTA per SM with twice the tile width -- measured slower (4096^2: 225 vs 208 us per
   // pass, same DRAM traffic; profiles/r01_notes.md session 4)
   if (wmax > W && getenv("GGP_STR_WIDE")) W = wmax;
-  if (const char* e = getenv("GGP_STR_W")) {  // tuning knob
+  // z axis of a 3-D grid: consecutive points of a line are a whole xy-plane apart (8 MB at 1024^3), so every row
+  // piece of the tile is its own DRAM page and TLB entry; 64-byte pieces instead of 32 halve that cost
+  // (1024^3 c64: z pass 17.2 -> 6.7 ms, step 29.4 -> 18.5 ms; 512^3: neutral; 128-byte pieces: slower again)
+  if (ax == 2) {
+    const int w64 = 64 / (int)sizeof(cpx<T>);
+    if (w64 > W && w64 <= wmax) W = w64;
+  }
+  if (const char* e = getenv(ax == 2 ? "GGP_STR_WZ" : "GGP_STR_W")) {  // tuning knobs (z axis of 3-D grids: GGP_STR_WZ)
     const int w = atoi(e);
     if (w >= 1 && w <= wmax && (w & (w - 1)) == 0) W = w;
   }
+  // the exchange lines of the whole tile must fit one CTA's shared memory
+  while (W > 1 && K::str_lines_bytes(M, W, K::str_ls(W)) > (size_t)200 * 1024) W >>= 1;
   while (W > nfast) W >>= 1;
   *W_ = W;
   *LS_ = K::str_ls(W);
@@ -106,7 +115,7 @@ template <typename T, int N, int M>
 static int launch_str_tma_m(StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS, threads, us;
-  str_query<T, N>(M, nfast, &W, &LS, &threads, &us);
+  str_query<T, N>(M, p.ax, nfast, &W, &LS, &threads, &us);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = LS;
@@ -139,7 +148,7 @@ template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS_, threads_, us_;
-  str_query<T, N>(M, nfast, &W, &LS_, &threads_, &us_);
+  str_query<T, N>(M, p.ax, nfast, &W, &LS_, &threads_, &us_);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = K::str_ls(W);
@@ -147,7 +156,7 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   size_t smem = K::USES_SMEM ? K::str_lines_bytes(M, W, p.LS) : 0;
   // CTAs per SM the register file allows with this geometry (the launch bounds cap the registers accordingly)
   int nb = K::str_min_blocks(M);
-  if (W * K::TPL > K::STR_THREADS) nb = K::str_bound_blocks(M);
+  if (W * K::TPL != K::STR_THREADS && K::data_regs(M) <= 32) nb = 1024 / (W * K::TPL) < 1 ? 1 : 1024 / (W * K::TPL);
   const size_t per_sm = 227 * 1024 - 1024;
   const size_t dl_bytes = (((size_t)N * sizeof(cpx<T>) + 15) & ~(size_t)15);
   p.tw_smem = 0;
@@ -175,6 +184,14 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   }
   const long long grid = p.ntx * nother;
   if (grid > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  // next-tile L2 prefetch (str_kernel): opt-in, GGP_STR_PF = distance in CTAs.  Measured SLOWER (4096^2: 228 -> 257 us
+  // per step with a distance of one wave, 8192^2: 1278 -> 1379): the prefetches compete with the demand loads for
+  // the same DRAM pages instead of hiding them (profiles/r01_notes.md, session 4)
+  p.pf_dist = 0;
+  {
+    static const int pf_env = getenv("GGP_STR_PF") ? atoi(getenv("GGP_STR_PF")) : 0;
+    if (p.tma && !p.scatter && pf_env > 0) p.pf_dist = pf_env;
+  }
   auto k = str_kernel<T, N, M>;
   int e = set_smem(k, smem);
   if (e) return e;
@@ -260,6 +277,6 @@ template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaS
 #ifdef GGP_TMA
 template int launch_str_tma<GGP_T, GGP_N>(int, StrTmaParams<GGP_T>, long long, long long, int, cudaStream_t);
 #endif
-template void str_query<GGP_T, GGP_N>(int, long long, int*, int*, int*, int*);
+template void str_query<GGP_T, GGP_N>(int, int, long long, int*, int*, int*, int*);
 
 }  // namespace ggp

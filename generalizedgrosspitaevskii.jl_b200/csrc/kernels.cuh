@@ -16,6 +16,9 @@
 #include "tma.cuh"
 
 #define GGP_MAX_PEERS 8
+#ifndef GGP_STOCH_BUDGET
+#define GGP_STOCH_BUDGET 128
+#endif
 #ifndef GGP_STR_D2_BLOCKS
 #define GGP_STR_D2_BLOCKS 2
 #endif
@@ -61,6 +64,8 @@ struct alignas(64) StrParams {
   long long dst_ls, dst_s1, dst_s2, dst_base;
   int scatter, dst_shift;
   int dl_smem;  // KIND_SEP: D_line is staged in shared memory behind the exchange lines (set by the launcher)
+  int pf_dist;  // > 0: while waiting for its own tile a CTA prefetches tile (blockIdx + pf_dist) into L2 -- set by the
+                // launcher to the number of resident CTAs when the state does not fit the L2 (see str_kernel)
   int tw_smem;  // twiddle table staged in shared memory although the compile-time default (str_tw_smem) says no:
                 // set by the launcher when the geometry chosen at run time (W, CTAs per SM) leaves room for it
 };
@@ -120,7 +125,7 @@ struct KCfg {
   // threads, one CTA per SM; GGP_STR_WIDE=1).  Not the default: at 4096^2 the wide tile is slower (225 vs 208 us)
   // and the DRAM traffic is the same 2x of the algorithmic bytes either way (ncu, profiles/r01_notes.md session 4).
   __host__ __device__ static constexpr int str_max_threads(int M) {
-    return (sizeof(T) == 4 && data_regs(M) <= 32 && STR_THREADS == 512) ? 1024 : STR_THREADS;
+    return (data_regs(M) <= 32 && STR_THREADS < 1024) ? 1024 : STR_THREADS;
   }
   __host__ __device__ static constexpr int str_bound_blocks(int M) {  // min CTAs per SM stated in the launch bounds
     return str_max_threads(M) > STR_THREADS ? 1 : str_min_blocks(M);
@@ -160,7 +165,7 @@ struct KCfg {
   // the two-component fp64 one (2 instead of 3 at 168) -- measured 17 % slower on C4 and C3.
   __host__ __device__ static constexpr int row_min_blocks(int M, int pwv) {
     const int dr = data_regs(M);
-    const int budget = dr <= 32 ? (pwv == PW_STOCH ? 128 : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pwv == PW_STOCH ? 255 : 168) : 255);
+    const int budget = dr <= 32 ? (pwv == PW_STOCH ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pwv == PW_STOCH ? 255 : 168) : 255);
     const int b = 65536 / (ROW_THREADS * budget);
     return b < 1 ? 1 : b;
   }
@@ -382,6 +387,21 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
           tma_load_4d(smem + ((size_t)c * N + r0) * p.W, &p.map[c], bar, (int)(2 * xt * p.W), p.ax == 1 ? r0 : (int)o1,
                       p.ax == 1 ? (int)o1 : r0, (int)o2);
     }
+    // States larger than the L2: the tile that the CTA taking over this SM slot will want (blockIdx + number of
+    // resident CTAs) is pulled into L2 now, while this CTA has nothing to do but wait for its own tile -- that
+    // later load then streams from L2 instead of paying one DRAM page miss per 16/32-byte row piece
+    // (ncu r01u, 4096^2: 26 % of the stall samples sit on the tile's mbarrier).
+    if (p.pf_dist) {
+      const long long g2 = g + p.pf_dist;
+      if (g2 < (long long)gridDim.x) {
+        const long long xt2 = g2 % p.ntx, oo = g2 / p.ntx;
+        const long long base = xt2 * p.W + (oo % p.no1) * p.s1 + (oo / p.no1) * p.s2;
+#pragma unroll 1
+        for (int c = 0; c < M; ++c)
+#pragma unroll 1
+          for (int r = threadIdx.x; r < N; r += blockDim.x) prefetch_l2(p.u[c] + base + (long long)r * p.ls);
+      }
+    }
     mbar_wait(bar, 0);
 #pragma unroll
     for (int c = 0; c < M; ++c)
@@ -543,6 +563,6 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
 // geometry of the strided kernels for a fast axis of nfast points: W (coalescing width), padded
 // line stride LS, threads per CTA, and whether the line needs the shared exchange buffer
 template <typename T, int N>
-void str_query(int M, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
+void str_query(int M, int ax, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
 
 }  // namespace ggp
