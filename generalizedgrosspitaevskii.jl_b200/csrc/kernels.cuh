@@ -16,6 +16,12 @@
 #include "tma.cuh"
 
 #define GGP_MAX_PEERS 8
+#ifndef GGP_ROW_PARK
+#define GGP_ROW_PARK 1
+#endif
+#ifndef GGP_PARK_BUDGET
+#define GGP_PARK_BUDGET 80
+#endif
 #ifndef GGP_STOCH_BUDGET
 #define GGP_STOCH_BUDGET 128
 #endif
@@ -163,7 +169,18 @@ struct KCfg {
   // The register budget is stated explicitly for every variant: left to itself with "at least one CTA" the
   // compiler spends 144 registers on the stochastic fp64 kernel (3 CTAs per SM instead of 4 at 128) and 190 on
   // the two-component fp64 one (2 instead of 3 at 168) -- measured 17 % slower on C4 and C3.
+  // Two components, deterministic half-steps: the row kernel keeps ONE component in registers at a time and parks
+  // the other in its (otherwise idle) exchange line -- half the registers, twice the resident CTAs, and one copy
+  // of the transform code instead of two (C3, ncu r01t: 168 registers = 12 warps per SM, 18 % of the stall samples
+  // `no_instructions`).  The stochastic variant keeps both components in registers (Philox words per element).
+  __host__ __device__ static constexpr bool row_parked(int M, int pwv) {
+    return GGP_ROW_PARK && M == 2 && pwv != PW_STOCH && USES_SMEM && data_regs(1) <= 32;
+  }
   __host__ __device__ static constexpr int row_min_blocks(int M, int pwv) {
+    if (row_parked(M, pwv)) {  // one component in registers at a time (row_parked_body)
+      const int bp = 65536 / (ROW_THREADS * GGP_PARK_BUDGET);
+      return bp < 1 ? 1 : bp;
+    }
     const int dr = data_regs(M);
     const int budget = dr <= 32 ? (pwv == PW_STOCH ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pwv == PW_STOCH ? 255 : 168) : 255);
     const int b = 65536 / (ROW_THREADS * budget);
@@ -265,6 +282,72 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
   }
 }
 
+// Row kernel body for two components with one component in registers at a time (KCfg::row_parked).
+//   phase 1: component 0: load, inverse FFT_x, park in its own exchange line (every thread parks and later reloads
+//            ITS OWN elements, positions t + m*TPL); component 1: load, inverse FFT_x, stays in registers
+//   point-wise: both half-steps element by element, component 0 read from / written back to the parked line
+//   phase 2: component 1: forward FFT_x, store; component 0: reload, forward FFT_x, store
+// The component loops are NOT unrolled: one copy of the transform code serves both.
+template <typename T, int N, int PWV>
+__device__ __forceinline__ void row_parked_body(const RowParams<T>& p, cpx<T>* sl, const int t, const bool active,
+                                                const long long goff, const long long soff) {
+  using K = KCfg<T, N>;
+  using L = LineCfg<T, N>;
+  constexpr int E = K::E, TPL = K::TPL, LS = K::row_ls();
+  using SYNC = typename K::RowSync;
+  cpx<T> a[E];
+  cpx<T>* const park = sl + L::pad(t);                  // pad(t + m*TPL) = pad(t) + m*(TPL + TPL/E) when TPL % E == 0
+  constexpr bool LIN = (TPL % E == 0);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) a[m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
+    if (p.flags & 1) {
+      conj_all<T, E>(a);
+      fft_line<T, N, -1, SYNC, true>(a, t, sl + c * LS, p.tw);
+      conj_all<T, E>(a);
+    }
+    if (c == 0) {
+      SYNC::sync();  // the last pass of the transform may still be reading this line
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        if constexpr (LIN) park[m * (TPL + TPL / E)] = a[m];
+        else sl[L::pad(t + m * TPL)] = a[m];
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+      cpx<T> f[2];
+      if constexpr (LIN) f[0] = park[m * (TPL + TPL / E)];
+      else f[0] = sl[L::pad(t + m * TPL)];
+      f[1] = a[m];
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+        if (p.hs[h].apply) half_step_point<T, 2, PWV>(f, p.pw, p.hs[h], soff + m * TPL, goff + m * TPL, nullptr);
+      if constexpr (LIN) park[m * (TPL + TPL / E)] = f[0];
+      else sl[L::pad(t + m * TPL)] = f[0];
+      a[m] = f[1];
+    }
+  }
+#pragma unroll 1
+  for (int c = 1; c >= 0; --c) {
+    if (c == 0) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        if constexpr (LIN) a[m] = park[m * (TPL + TPL / E)];
+        else a[m] = sl[L::pad(t + m * TPL)];
+      }
+    }
+    if (p.flags & 2) fft_line<T, N, -1, SYNC, true>(a, t, sl + c * LS, p.tw);  // PRESYNC: everybody has reloaded
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) p.u[c][goff + m * TPL] = a[m];
+    }
+  }
+}
+
 // flags: bit 0 = PRE (inverse FFT_x before the half-steps), bit 1 = POST (forward FFT_x after)
 template <typename T, int N, int M, int PWV>
 __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_blocks(M, PWV)) row_kernel(const RowParams<T> p) {
@@ -283,22 +366,26 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
 
   pdl_launch_dependents();
   pdl_wait();
-  cpx<T> v[M][E];
-#pragma unroll
-  for (int c = 0; c < M; ++c)
-#pragma unroll
-    for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
-
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 0);
-    if (it == 0 && active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 2, soff, goff, TPL);
-  }
-  if (active) {
+  if constexpr (K::row_parked(M, PWV)) {
+    row_parked_body<T, N, PWV>(p, sl, t, active, goff, soff);
+  } else {
+    cpx<T> v[M][E];
 #pragma unroll
     for (int c = 0; c < M; ++c)
 #pragma unroll
-      for (int m = 0; m < E; ++m) p.u[c][goff + m * TPL] = v[c][m];
+      for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
+
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 0);
+      if (it == 0 && active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 2, soff, goff, TPL);
+    }
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < M; ++c)
+#pragma unroll
+        for (int m = 0; m < E; ++m) p.u[c][goff + m * TPL] = v[c][m];
+    }
   }
 }
 
