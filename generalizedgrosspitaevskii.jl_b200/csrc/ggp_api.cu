@@ -101,7 +101,7 @@ static void dispatch_str_query(int N, int M, int ax, long long nfast, int* W, in
   switch (N) {
 #define X(n)                                   \
   case n:                                      \
-    str_query<T, n>(M, ax, nfast, W, LS, threads, us); \
+    str_query<T, n>(M, ax, 0, nfast, W, LS, threads, us); \
     return;
     GGP_SIZES(X)
 #undef X
@@ -937,6 +937,7 @@ struct PlanT : PlanBase {
     }
     p.mode = mode;
     p.ax = ax;
+    p.slab = slab ? 1 : 0;
     long long nother;
     if (ax == 1) {
       p.ls = g0;

@@ -83,7 +83,7 @@ int launch_row(int M, int pwv, const RowParams<T>& p, cudaStream_t st) {
 }
 
 template <typename T, int N>
-void str_query(int M, int ax, long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
+void str_query(int M, int ax, int slab, long long nfast, int* W_, int* LS_, int* threads, int* uses_smem) {
   using K = KCfg<T, N>;
   const int wmax = K::str_max_threads(M) / K::TPL;
   int W = K::WDEF;
@@ -96,6 +96,14 @@ void str_query(int M, int ax, long long nfast, int* W_, int* LS_, int* threads, 
   if (ax == 2) {
     const int w64 = 64 / (int)sizeof(cpx<T>);
     if (w64 > W && w64 <= wmax) W = w64;
+  }
+  // slab-decomposed plans: the tile is read with plain coalesced loads and half of it leaves as peer stores over
+  // NVLink -- 128-byte row pieces (one full line per load / per NVLink write) instead of 32/64
+  // (2 x B200, 512^3: 1.72 -> 1.28 ms/step; 1024^3: 16.7 -> 11.0 ms/step)
+  if (slab) {
+    int w128 = 128 / (int)sizeof(cpx<T>);
+    while (w128 > wmax) w128 >>= 1;
+    if (w128 > W) W = w128;
   }
   if (const char* e = getenv(ax == 2 ? "GGP_STR_WZ" : "GGP_STR_W")) {  // tuning knobs (z axis of 3-D grids: GGP_STR_WZ)
     const int w = atoi(e);
@@ -115,7 +123,7 @@ template <typename T, int N, int M>
 static int launch_str_tma_m(StrTmaParams<T> p, long long nfast, long long nother, int sm_count, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS, threads, us;
-  str_query<T, N>(M, p.ax, nfast, &W, &LS, &threads, &us);
+  str_query<T, N>(M, p.ax, 0, nfast, &W, &LS, &threads, &us);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = LS;
@@ -148,7 +156,7 @@ template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
   int W, LS_, threads_, us_;
-  str_query<T, N>(M, p.ax, nfast, &W, &LS_, &threads_, &us_);
+  str_query<T, N>(M, p.ax, p.slab, nfast, &W, &LS_, &threads_, &us_);
   p.W = W;
   p.logW = ilog2(W);
   p.LS = K::str_ls(W);
@@ -277,6 +285,6 @@ template int launch_oned<GGP_T, GGP_N>(int, int, const OneDParams<GGP_T>&, cudaS
 #ifdef GGP_TMA
 template int launch_str_tma<GGP_T, GGP_N>(int, StrTmaParams<GGP_T>, long long, long long, int, cudaStream_t);
 #endif
-template void str_query<GGP_T, GGP_N>(int, int, long long, int*, int*, int*, int*);
+template void str_query<GGP_T, GGP_N>(int, int, int, long long, int*, int*, int*, int*);
 
 }  // namespace ggp

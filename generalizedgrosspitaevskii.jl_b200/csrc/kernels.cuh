@@ -70,6 +70,7 @@ struct alignas(64) StrParams {
   long long dst_ls, dst_s1, dst_s2, dst_base;
   int scatter, dst_shift;
   int dl_smem;  // KIND_SEP: D_line is staged in shared memory behind the exchange lines (set by the launcher)
+  int slab;     // slab-decomposed plan (LDG loads, peer stores): the launcher picks 128-byte tiles
   int pf_dist;  // > 0: while waiting for its own tile a CTA prefetches tile (blockIdx + pf_dist) into L2 -- set by the
                 // launcher to the number of resident CTAs when the state does not fit the L2 (see str_kernel)
   int tw_smem;  // twiddle table staged in shared memory although the compile-time default (str_tw_smem) says no:
@@ -650,6 +651,6 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
 // geometry of the strided kernels for a fast axis of nfast points: W (coalescing width), padded
 // line stride LS, threads per CTA, and whether the line needs the shared exchange buffer
 template <typename T, int N>
-void str_query(int M, int ax, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
+void str_query(int M, int ax, int slab, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
 
 }  // namespace ggp
