@@ -622,6 +622,18 @@ struct PlanT : PlanBase {
           for (int c = 0; c < d.pump_ncomp; ++c) pw.S_const[c] = mk<T>((T)v0[c].real(), (T)v0[c].imag());
         }
       }
+      if (d.pump_ncomp == 2 && !pw.pump_const) {
+        // a component whose profile is identically zero (the exciton component of examples/exciton_polariton.jl:55-59)
+        // is never read by the kernels
+        for (int c = 0; c < 2; ++c) {
+          bool zero = true;
+          for (long long i = 0; i < nspatial && zero; ++i) {
+            if (d.table_precision == GGP_C128) zero = ((const std::complex<double>*)d.pump_table)[i * 2 + c] == std::complex<double>(0, 0);
+            else zero = ((const std::complex<float>*)d.pump_table)[i * 2 + c] == std::complex<float>(0, 0);
+          }
+          pw.pump_zero[c] = zero ? 1 : 0;
+        }
+      }
       pw.S[0] = S[0];
       pw.S[1] = S[1];
       amp_prev = std::complex<double>(d.pump_amp0[0], d.pump_amp0[1]);
@@ -1149,7 +1161,7 @@ struct PlanT : PlanBase {
 
   // which compile-time variant of the half-step covers this problem (pointwise.cuh)
   int pw_variant() const {
-    if (pw.noise) return PW_STOCH;
+    if (pw.noise) return pw.noise_field ? PW_FIELD : PW_STOCH;
     if (pw.vkind || pw.pump || pw.nl != 1) return PW_DET;
     return PW_KERR;
   }

@@ -72,7 +72,8 @@ template <typename T, int N, int M>
 static int launch_row_m(int pwv, const RowParams<T>& p, cudaStream_t st) {
   if (pwv == PW_KERR) return launch_row_mp<T, N, M, PW_KERR>(p, st);
   if (pwv == PW_DET) return launch_row_mp<T, N, M, PW_DET>(p, st);
-  return launch_row_mp<T, N, M, PW_STOCH>(p, st);
+  if (pwv == PW_STOCH) return launch_row_mp<T, N, M, PW_STOCH>(p, st);
+  return launch_row_mp<T, N, M, PW_FIELD>(p, st);
 }
 
 template <typename T, int N>
@@ -229,7 +230,8 @@ template <typename T, int N, int M>
 static int launch_oned_m(int pwv, const OneDParams<T>& p, cudaStream_t st) {
   if (pwv == PW_KERR) return launch_oned_mp<T, N, M, PW_KERR>(p, st);
   if (pwv == PW_DET) return launch_oned_mp<T, N, M, PW_DET>(p, st);
-  return launch_oned_mp<T, N, M, PW_STOCH>(p, st);
+  if (pwv == PW_STOCH) return launch_oned_mp<T, N, M, PW_STOCH>(p, st);
+  return launch_oned_mp<T, N, M, PW_FIELD>(p, st);
 }
 
 template <typename T, int N>

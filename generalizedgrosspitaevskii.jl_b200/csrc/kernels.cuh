@@ -175,7 +175,7 @@ struct KCfg {
   // of the transform code instead of two (C3, ncu r01t: 168 registers = 12 warps per SM, 18 % of the stall samples
   // `no_instructions`).  The stochastic variant keeps both components in registers (Philox words per element).
   __host__ __device__ static constexpr bool row_parked(int M, int pwv) {
-    return GGP_ROW_PARK && M == 2 && pwv != PW_STOCH && USES_SMEM && data_regs(1) <= 32;
+    return GGP_ROW_PARK && M == 2 && !pw_is_stoch(pwv) && USES_SMEM && data_regs(1) <= 32;
   }
   __host__ __device__ static constexpr int row_min_blocks(int M, int pwv) {
     if (row_parked(M, pwv)) {  // one component in registers at a time (row_parked_body)
@@ -183,7 +183,7 @@ struct KCfg {
       return bp < 1 ? 1 : bp;
     }
     const int dr = data_regs(M);
-    const int budget = dr <= 32 ? (pwv == PW_STOCH ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pwv == PW_STOCH ? 255 : 168) : 255);
+    const int budget = dr <= 32 ? (pw_is_stoch(pwv) ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pw_is_stoch(pwv) ? 255 : 168) : 255);
     const int b = 65536 / (ROW_THREADS * budget);
     return b < 1 ? 1 : b;
   }
@@ -217,7 +217,7 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
                                            const HalfStep<T>* hs, const int nh, const long long sidx0,
                                            const long long gidx0, const long long stride) {
   constexpr int E = LineCfg<T, N>::E;
-  if constexpr (PWV == PW_STOCH) {
+  if constexpr (pw_is_stoch(PWV)) {
     // All Philox words of this thread first (E*M independent chains: good ILP), one call per element and
     // component serving both half-steps of the pair; then the half-steps as in the deterministic variant.
     uint4 rnd[E][M];

@@ -35,6 +35,7 @@ struct PointwiseParams {
   int pump;    // 0 none, 1 scalar broadcast (S[0] for every component), 2 per component
   int pump_const;      // the pump profile is the same at every grid point (e.g. examples/truncated_wigner.jl:37-39):
   cpx<T> S_const[2];   // its value rides in the parameters and the table is not read
+  int pump_zero[2];    // per-component pump (pump == 2): this component's profile is identically zero, skip its loads
   int nl;      // 0 none, 1 real coefficients, 2 complex coefficients
   T nl_c_re[2], nl_c_im[2];
   T nl_g_re[2][2], nl_g_im[2][2];
@@ -154,8 +155,11 @@ __device__ __forceinline__ cpx<T> normal_from(const uint4 r, uint32_t ctr, int r
 // footprint, see profiles/r01_notes.md):
 //   PW_KERR   real diagonal nonlinearity only (C1, C2, C5: scalar Kerr GPE)
 //   PW_DET    + complex nonlinearity, potential table (any kind), separable pump   (C3, bistability)
-//   PW_STOCH  + position noise (host-fed or Philox)                                (C4, windowed FT)
-enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2 };
+//   PW_STOCH  + position noise (host-fed or Philox), constant amplitude            (C4, windowed FT)
+//   PW_FIELD  + field- / position-dependent noise amplitude (GGP_NOISE_FIELD); its own variant because the extra
+//             live values cost the constant-amplitude kernel 4 % when they shared one (C4: 8.52 -> 8.88 ms/step)
+enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2, PW_FIELD = 3 };
+__host__ __device__ constexpr bool pw_is_stoch(int pwv) { return pwv >= PW_STOCH; }
 
 // One real-space half-step at one grid point.  sidx: index into the spatial tables; gidx: local
 // element index (spatial + batch) for noise.
@@ -179,20 +183,17 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
   }
   // field-dependent noise amplitude: |u_j| of the PRE-update field (src/kernels.jl:40-42)
   cpx<T> etav[M];
-  if (PWV == PW_STOCH && p.noise) {
+  if constexpr (PWV == PW_FIELD) {
+    T av[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) etav[i] = p.eta[i];
-    if (p.noise_field) {
-      T av[M];
+    for (int j = 0; j < M; ++j) av[j] = sqrt(cabs2(f[j]));
 #pragma unroll
-      for (int j = 0; j < M; ++j) av[j] = sqrt(cabs2(f[j]));
+    for (int i = 0; i < M; ++i) {
+      etav[i] = p.eta[i];
 #pragma unroll
-      for (int i = 0; i < M; ++i) {
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-          etav[i] = mk<T>(fma_(p.alpha[i][j].x, av[j], etav[i].x), fma_(p.alpha[i][j].y, av[j], etav[i].y));
-        if (p.nprof) etav[i] = cmul(p.nprof[sidx % p.n1], etav[i]);
-      }
+      for (int j = 0; j < M; ++j)
+        etav[i] = mk<T>(fma_(p.alpha[i][j].x, av[j], etav[i].x), fma_(p.alpha[i][j].y, av[j], etav[i].y));
+      if (p.nprof) etav[i] = cmul(p.nprof[sidx % p.n1], etav[i]);
     }
   }
   // nonlinear phase on the pre-update field, kept as ph = cis(-dt G) - 1
@@ -223,7 +224,8 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
   if (p.pump) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j] : p.S[p.pump == 1 ? 0 : j][sidx];
+      sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j]
+                           : ((p.pump == 2 && p.pump_zero[j]) ? mk<T>((T)0, (T)0) : p.S[p.pump == 1 ? 0 : j][sidx]);
       w[j] = f[j] + cmul(h.fnow, sv[j]);
     }
   } else {
@@ -254,7 +256,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
 #pragma unroll
     for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, sv[i]);
   }
-  if (PWV == PW_STOCH && p.noise) {
+  if (pw_is_stoch(PWV) && p.noise) {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       cpx<T> xi;
@@ -264,7 +266,9 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
         xi = normal_from<T>(rnd[i], h.ctr, p.noise_real);
       }
       // -i sqrt(dt) eta xi
-      const cpx<T> ex = cmul(etav[i], xi);
+      cpx<T> ex;
+      if constexpr (PWV == PW_FIELD) ex = cmul(etav[i], xi);
+      else ex = cmul(p.eta[i], xi);
       res[i] = res[i] + mk<T>(p.sqrt_dt * ex.y, -p.sqrt_dt * ex.x);
     }
   }

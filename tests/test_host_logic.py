@@ -177,3 +177,29 @@ def test_pump_schedule_matches_oracle_times(G):
         t = t + dt
         mine.append((t + dt / 2, t + dt))
     assert np.array_equal(np.array(mine), tt)
+
+
+def test_separable_dispersion_hint(G):
+    """`disp_sep_tol` (include/ggp.h): a ComplexF32 table of a dispersion that is a sum over axes gets the measured
+    deviation of the table from the product of its own axis factors (its rounding, growing with the phase); anything
+    that is not a sum over axes in Float64 arithmetic, or not scalar, gets 0 = library default."""
+    import importlib
+    host = importlib.import_module("ggp_b200.host")
+    tols = []
+    for N in (64, 512):
+        pb = P.kerr2d(G, N=N, dtype=np.complex64, nsteps=4)
+        prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+        rg = G.reciprocal_grid(prob)
+        kind, tab = host.exp_table(prob.dispersion, rg, prob.param, pb["dt"], 1)
+        assert tab.dtype == np.complex64
+        tol = host.separable_dispersion_tol(prob.dispersion, rg, prob.param, tab)
+        t2 = tab.reshape(N, N)
+        dev = np.abs(t2 - np.outer(t2[:, 0] / t2[0, 0], t2[0, :])).max()
+        assert dev <= tol <= 2 * dev + 1e-8
+        tols.append(tol)
+    assert tols[1] > tols[0]                                   # eps32 * |phase|: larger grid, larger phase
+    coupled = lambda ks, p: (ks[0] ** 2 + ks[1] ** 2) / 2 + 1e-4 * ks[0] * ks[1]
+    assert host.separable_dispersion_tol(coupled, rg, prob.param, tab) == 0.0
+    vec = lambda ks, p: G.SVector((ks[0] ** 2 + ks[1] ** 2) / 2)
+    assert host.separable_dispersion_tol(vec, rg, prob.param, tab) == 0.0
+    assert host.separable_dispersion_tol(prob.dispersion, rg[:1], prob.param, tab[:N]) == 0.0   # 1-D: nothing to factor
