@@ -26,6 +26,9 @@ CASES = {
     "windowed_ft_noise": ("windowed_ft", dict(ntraj=8), 11),
     "truncated_wigner_2d_noise": ("truncated_wigner", dict(ntraj=4, N=16, ndim=2, tspan=(0, 0.5)), 5),
     "kerr3d_c128": ("kerr3d", dict(N=8, dtype="complex128", nsteps=4, L=8.0), None),
+    # field- and position-dependent noise amplitudes (docs/src/stochastic_simulations.md:62-86)
+    "noise_field_1d": ("noise_forms", dict(form="field", ndim=1, M=1, N=32, ntraj=3), 7),
+    "noise_profile_q2_2d_two_comp": ("noise_forms", dict(form="both", ndim=2, M=2, N=16, ntraj=2), 9),
 }
 
 
