@@ -15,7 +15,7 @@ TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL = 0, 1, 2, 3
 NL_NONE, NL_DIAG = 0, 1
 PUMP_NONE, PUMP_SEPARABLE = 0, 1
 NOISE_NONE, NOISE_CONST, NOISE_FIELD = 0, 1, 2
-OBS_DENSITY, OBS_MOMENTUM, OBS_NORM = 0, 1, 2
+OBS_DENSITY, OBS_MOMENTUM, OBS_NORM, OBS_G2_MOMENTUM = 0, 1, 2, 3
 
 EXPORTS = [
     "ggp_version", "ggp_device_count", "ggp_last_error", "ggp_plan_create", "ggp_plan_destroy",

@@ -173,6 +173,42 @@ __global__ void sum_kernel(const double* __restrict__ in, double* __restrict__ o
   if (threadIdx.x == 0) atomicAdd(out, sh[0]);
 }
 
+// Second moment of the momentum occupation over the trajectories of a 1-D ensemble (the double loop `G2` of
+// examples/truncated_wigner.jl:143-154 without its O(N^2 B) host pass):
+//   out[m*N + n] += scale * sum_{t in this z-slice} |u~_t[m]|^2 |u~_t[n]|^2
+// u~ is the transformed state (natural order).  16x16 output tile per CTA, trajectories in chunks of 16 through
+// shared memory, blockIdx.z splits the trajectories; fp64 accumulation, one atomicAdd per output and z-slice.
+template <typename T>
+__global__ void g2_kernel(const cpx<T>* __restrict__ u, double* __restrict__ out, int N, long long nbatch, double scale) {
+  __shared__ double Im[16][17], In[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+  const long long per = (nbatch + gridDim.z - 1) / gridDim.z;
+  const long long t0 = (long long)blockIdx.z * per, t1 = t0 + per < nbatch ? t0 + per : nbatch;
+  double acc = 0;
+  for (long long tb = t0; tb < t1; tb += 16) {
+    const long long t = tb + ty;
+    double im = 0, in = 0;
+    if (t < t1) {
+      if (m0 + tx < N) {
+        const cpx<T> z = u[t * N + m0 + tx];
+        im = (double)z.x * (double)z.x + (double)z.y * (double)z.y;
+      }
+      if (n0 + tx < N) {
+        const cpx<T> z = u[t * N + n0 + tx];
+        in = (double)z.x * (double)z.x + (double)z.y * (double)z.y;
+      }
+    }
+    Im[ty][tx] = im;
+    In[ty][tx] = in;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += Im[k][ty] * In[k][tx];
+    __syncthreads();
+  }
+  if (m0 + ty < N && n0 + tx < N) atomicAdd(out + (size_t)(m0 + ty) * N + n0 + tx, acc * scale);
+}
+
 // Cross-GPU barrier of the slab decomposition (one CTA, lane q talks to rank q): publish this rank's epoch in
 // every peer's flag array (a release store at system scope; the peer stores of the preceding kernel are complete
 // at its end), then wait until every peer has published the same epoch in ours.  Bounded spin: a rank that died
@@ -303,6 +339,7 @@ struct PlanT : PlanBase {
   size_t hs_cap = 0;
   void* xi_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   double* obs_dev = nullptr;
+  double* g2_dev = nullptr;  // M * N * N doubles, allocated on first use (GGP_OBS_G2_MOMENTUM)
   cpx<T>* scratch[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   // 3-D slab decomposition (one process per GPU): this rank holds z-planes [prank*n3loc, (prank+1)*n3loc) of the
@@ -1267,6 +1304,7 @@ struct PlanT : PlanBase {
     const int threads = 256;
     const unsigned blocks = (unsigned)((nspatial + threads - 1) / threads);
     size_t count = 0;
+    double* result = obs_dev;
     if (kind == GGP_OBS_DENSITY) {
       for (int c = 0; c < M; ++c) {
         density_kernel<T><<<blocks, threads, 0, stream>>>(u[c], obs_dev + c * nspatial, nspatial, nbatch, 1.0);
@@ -1306,17 +1344,43 @@ struct PlanT : PlanBase {
         GGP_CUDA(cudaMemcpyAsync(u[c], scratch[c], bytes, cudaMemcpyDeviceToDevice, stream));
       }
       count = (size_t)(nspatial * M);
+    } else if (kind == GGP_OBS_G2_MOMENTUM) {
+      if (ndim != 1 || slab) return fail(GGP_ERR_UNSUPPORTED, "the G2 observable is defined for 1-D ensembles (N x N output)");
+      if (!size_supported(n[0])) return fail(GGP_ERR_UNSUPPORTED, "momentum observables need power-of-two axes");
+      const int N = (int)n[0];
+      const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch;
+      int rc;
+      if (!g2_dev && (rc = dalloc((void**)&g2_dev, sizeof(double) * (size_t)M * N * N))) return rc;
+      GGP_CUDA(cudaMemsetAsync(g2_dev, 0, sizeof(double) * (size_t)M * N * N, stream));
+      for (int c = 0; c < M; ++c) {
+        if (!scratch[c] && (rc = dalloc((void**)&scratch[c], bytes))) return rc;
+        GGP_CUDA(cudaMemcpyAsync(scratch[c], u[c], bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+      HalfStep<T> none;
+      memset(&none, 0, sizeof(none));
+      if ((rc = run_row(false, true, none, none))) return rc;
+      const double sc = 1.0 / ((double)N * N * (double)N * N);   // (fft / N) as in examples/truncated_wigner.jl:110
+      const unsigned tiles = (unsigned)((N + 15) / 16);
+      unsigned zs = (unsigned)std::min<long long>(64, (nbatch + 255) / 256);
+      if (zs < 1) zs = 1;
+      for (int c = 0; c < M; ++c) {
+        g2_kernel<T><<<dim3(tiles, tiles, zs), dim3(16, 16), 0, stream>>>(u[c], g2_dev + (size_t)c * N * N, N, nbatch, sc);
+        ++launches;
+        GGP_CUDA(cudaMemcpyAsync(u[c], scratch[c], bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+      count = (size_t)M * N * N;
+      result = g2_dev;
     } else {
       return fail(GGP_ERR_INVALID, "unknown observable kind");
     }
     GGP_CUDA(cudaGetLastError());
 #ifdef GGP_WITH_NCCL
     if (comm && nranks > 1) {
-      ncclResult_t r = ncclAllReduce(obs_dev, obs_dev, count, ncclDouble, ncclSum, comm, stream);
+      ncclResult_t r = ncclAllReduce(result, result, count, ncclDouble, ncclSum, comm, stream);
       if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
     }
 #endif
-    GGP_CUDA(cudaMemcpyAsync(out, obs_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+    GGP_CUDA(cudaMemcpyAsync(out, result, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
     GGP_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }

@@ -797,10 +797,14 @@ class StrangSplittingIterator:
         shape = self.u[0].shape[self.u[0].ndim - self.prob.ndim:]
         nspatial = int(np.prod(shape))
         n = self.M if kind == L.OBS_NORM else self.M * nspatial
+        if kind == L.OBS_G2_MOMENTUM:
+            n = self.M * nspatial * nspatial
         out = np.empty(n, dtype=np.float64)
         L.check(self.lib.ggp_observe(self.handle, kind, out.ctypes.data))
         if kind == L.OBS_NORM:
             return out
+        if kind == L.OBS_G2_MOMENTUM:                     # [c][m][n] = sum_traj |F_c(m)|^2 |F_c(n)|^2, F = fft(u_c)/N
+            return out.reshape(self.M, nspatial, nspatial)
         return out.reshape((self.M,) + tuple(shape))
 
 

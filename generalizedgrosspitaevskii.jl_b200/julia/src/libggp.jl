@@ -96,6 +96,15 @@ function ggp_save_async(h::Ptr{Cvoid}, dest::NTuple{M,Any}) where {M}
 end
 ggp_save_wait(h::Ptr{Cvoid}) = _check(ccall(_sym(:ggp_save_wait), Cint, (Ptr{Cvoid},), h))
 
+# Ensemble observables summed over the plan's trajectories on the device (all-reduced over ranks when a
+# communicator is attached): kind 0 density, 1 n(k) = Σ|fft(u)/N|², 2 norm, 3 Σ|F(m)|²|F(n)|² (1-D, the trajectory
+# sum inside `G2` of examples/truncated_wigner.jl:143-154).  `out` must hold M·nspatial (0, 1), M (2) or M·N² (3) doubles.
+const GGP_OBS_DENSITY, GGP_OBS_MOMENTUM, GGP_OBS_NORM, GGP_OBS_G2_MOMENTUM = Cint(0), Cint(1), Cint(2), Cint(3)
+function ggp_observe!(out::Array{Float64}, h::Ptr{Cvoid}, kind::Cint)
+    GC.@preserve out _check(ccall(_sym(:ggp_observe), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, kind, pointer(out)))
+    out
+end
+
 # Checkpoint / resume (include/ggp.h): fields + Philox counter word + F_now amplitude as one byte vector
 function ggp_checkpoint(h::Ptr{Cvoid})
     n = ccall(_sym(:ggp_checkpoint_bytes), Int64, (Ptr{Cvoid},), h)

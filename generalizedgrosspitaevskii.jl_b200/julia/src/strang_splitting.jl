@@ -157,3 +157,18 @@ function restore!(iter::StrangSplittingIterator, blob::Vector{UInt8})
     iter.step_index = Int(reinterpret(Int64, blob[end-7:end])[1])
     iter
 end
+
+# On-device ensemble observables (SURVEY §8f N1): `observe(iter, :momentum)` returns Σ_traj |fft(u_c)/N|² per component
+# without downloading the ensemble; `:g2` the N×N trajectory sum of examples/truncated_wigner.jl:143-154 (1-D).
+function observe(iter::StrangSplittingIterator, what::Symbol)
+    N = length(iter.prob.lengths); M = length(iter.prob.u0)
+    sz = size(first(iter.prob.u0))[1:N]
+    if what === :norm
+        return ggp_observe!(zeros(Float64, M), iter.handle, GGP_OBS_NORM)
+    elseif what === :g2
+        N == 1 || error("g2 is defined for 1-D ensembles")
+        return ggp_observe!(zeros(Float64, sz[1], sz[1], M), iter.handle, GGP_OBS_G2_MOMENTUM)   # [n, m, c] (symmetric in m, n)
+    end
+    kind = what === :density ? GGP_OBS_DENSITY : what === :momentum ? GGP_OBS_MOMENTUM : error("unknown observable $what")
+    ggp_observe!(zeros(Float64, sz..., M), iter.handle, kind)
+end

@@ -82,7 +82,11 @@ typedef enum ggp_noise_kind {
 typedef enum ggp_observable {
   GGP_OBS_DENSITY = 0,  /* out[c][r] = sum over local trajectories |u_c(r)|^2        (double, M*nspatial) */
   GGP_OBS_MOMENTUM = 1, /* out[c][k] = sum over local trajectories |fft(u_c)(k)|^2/N^2 (double, M*nspatial) */
-  GGP_OBS_NORM = 2      /* out[c]    = sum over everything |u_c|^2                    (double, M) */
+  GGP_OBS_NORM = 2,     /* out[c]    = sum over everything |u_c|^2                    (double, M) */
+  GGP_OBS_G2_MOMENTUM = 3 /* 1-D ensembles: out[c][m][n] = sum over local trajectories |F_c(m)|^2 |F_c(n)|^2 with
+                             F = fft(u_c)/N  (double, M*N*N): the trajectory sum inside `G2` of
+                             examples/truncated_wigner.jl:143-154; the Wigner-ordering corrections of `f` (:139-141)
+                             are a host-side combination of this matrix with n(k) = GGP_OBS_MOMENTUM */
 } ggp_observable;
 
 typedef struct ggp_desc {

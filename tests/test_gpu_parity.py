@@ -349,3 +349,33 @@ def test_observables(G):
     # the state is untouched by observing
     assert np.array_equal(it.fetch()[0], u)
     it.close()
+
+
+@pytest.mark.parametrize("ntraj,N,dtype", [(37, 64, np.complex128), (600, 256, np.complex128), (50, 32, np.complex64)])
+def test_g2_momentum_observable(G, ntraj, N, dtype):
+    """the trajectory sum of examples/truncated_wigner.jl:143-154 (`G2`) on the device, against the
+    example's own host formulas -- raw second moment, then g2(k,k') with the Wigner-ordering corrections of `f`."""
+    pb = P.truncated_wigner(G, ntraj=ntraj, N=N, ndim=1, dtype=dtype, tspan=(0, 0.5))
+    prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    it = G.init(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=1, save_start=False, rng=3)
+    it.advance(4)
+    u = np.array(it.fetch()[0]).astype(np.complex128)                    # (ntraj, N)
+    raw = it.observe(G.lib.OBS_G2_MOMENTUM)[0]
+    nk = it.observe(G.lib.OBS_MOMENTUM)[0]
+    assert np.array_equal(np.array(it.fetch()[0]).astype(np.complex128), u)        # observing leaves the state alone
+    it.close()
+    inten = np.abs(np.fft.fft(u, axis=-1) / N) ** 2                        # |ft_sol|^2, ft_sol = fft(sol, 1) / N  (:110)
+    ref_raw = inten.T @ inten
+    tol = 1e-10 if dtype == np.complex128 else 2e-5
+    assert np.allclose(raw, ref_raw, rtol=tol, atol=tol * ref_raw.max())
+    assert np.allclose(nk, inten.sum(0), rtol=tol, atol=tol * inten.sum(0).max())
+    # the example's G2 / g2 from the two device observables (commutator = 1/L, :139-156)
+    Lbox = float(pb["lengths"][0])
+    cm = 1.0 / Lbox
+    delta = np.eye(N)
+    G2_dev = (raw - (1 + delta) * cm / 2 * (nk[:, None] + nk[None, :] - ntraj * cm / 2)) / ntraj
+    G2_ref = np.empty((N, N))
+    for m in range(N):
+        for n in range(N):
+            G2_ref[m, n] = np.mean(inten[:, m] * inten[:, n] - (1 + (m == n)) * cm / 2 * (inten[:, m] + inten[:, n] - cm / 2))
+    assert np.allclose(G2_dev, G2_ref, rtol=1e3 * tol, atol=1e3 * tol * np.abs(G2_ref).max())
