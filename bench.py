@@ -62,6 +62,13 @@ def make_workload(ns, name, nbatch=None, n=None, traj_range=None):
                                  "dispersion, time-dependent pump (BASELINE.json configs[2])",
                         grid=[N, N], ncomp=2, nbatch=1, dtype="c128", points=N * N,
                         bytes_row=2 * 2 * 16 + 2 * 16, bytes_str=2 * 2 * 16 + 64, b_alg_contract=288)
+    if name == "c3_c64":
+        N = n or 1024
+        pb = P.exciton_polariton(ns, N=N, nsaves=1, tspan=(0, 100), dt=0.05, time_pump=True, dtype=np.complex64)
+        return pb, dict(workload=f"C3 in ComplexF32: two-component exciton-polariton {N}^2, 2x2 matrix-exponential "
+                                 "dispersion, time-dependent pump",
+                        grid=[N, N], ncomp=2, nbatch=1, dtype="c64", points=N * N,
+                        bytes_row=2 * 2 * 8 + 2 * 8, bytes_str=2 * 2 * 8 + 32, b_alg_contract=144)
     if name == "c4":
         nb = nbatch or 4096
         pb = P.truncated_wigner(ns, ntraj=nb, N=256, ndim=2, dtype=np.complex128, tspan=(0, 20), dt=0.05,
@@ -509,6 +516,15 @@ def main():
                 r3["iter"].close()
             except Exception as e:
                 extra["c3"] = dict(error=repr(e))
+            try:
+                r3 = measure(G, "c3_c64", 200, 5, local, do_e2e=False, do_flush=False)
+                ms3 = r3["chained_ms"]
+                extra["c3_c64"] = dict(workload=r3["meta"]["workload"], value=r3["meta"]["points"] * 200 / (ms3 * 1e-3),
+                                       unit=METRIC, ms_per_step=ms3 / 200,
+                                       frac_of_hbm_roofline_contract=144 * r3["meta"]["points"] / (ms3 / 200 * 1e-3) / 1e9 / peak)
+                r3["iter"].close()
+            except Exception as e:
+                extra["c3_c64"] = dict(error=repr(e))
     if extra:
         line["extra"] = extra
 

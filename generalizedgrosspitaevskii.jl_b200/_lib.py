@@ -23,7 +23,7 @@ EXPORTS = [
     "ggp_comm_unique_id", "ggp_comm_init", "ggp_slab_ipc_export", "ggp_slab_ipc_attach", "ggp_state_device_ptr", "ggp_timer_begin", "ggp_timer_end",
     "ggp_launch_count", "ggp_host_alloc", "ggp_host_free", "ggp_device_bytes", "ggp_profile_enable",
     "ggp_profile_read", "ggp_debug_l2_flush", "ggp_debug_flush_only",
-    "ggp_save_async", "ggp_save_wait", "ggp_checkpoint_bytes", "ggp_checkpoint_save", "ggp_checkpoint_load",
+    "ggp_observe_windowed", "ggp_save_async", "ggp_save_wait", "ggp_checkpoint_bytes", "ggp_checkpoint_save", "ggp_checkpoint_load",
 ]
 
 
@@ -87,6 +87,7 @@ def load():
     lib.ggp_checkpoint_save.argtypes = [vp, vp, C.c_uint64]
     lib.ggp_checkpoint_load.argtypes = [vp, vp, C.c_uint64]
     lib.ggp_observe.argtypes = [vp, C.c_int, vp]
+    lib.ggp_observe_windowed.argtypes = [vp, vp, vp, vp]
     lib.ggp_comm_unique_id.argtypes = [vp]
     lib.ggp_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.ggp_slab_ipc_export.argtypes = [vp, vp]

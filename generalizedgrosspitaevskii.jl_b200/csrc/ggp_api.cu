@@ -209,6 +209,55 @@ __global__ void g2_kernel(const cpx<T>* __restrict__ u, double* __restrict__ out
   if (m0 + ty < N && n0 + tx < N) atomicAdd(out + (size_t)(m0 + ty) * N + n0 + tx, acc * scale);
 }
 
+// u[t][p] <- src[t][p] * w[p]   (window of the windowed Fourier transform, test/windowed_ft.jl:32-33)
+template <typename T>
+__global__ void window_kernel(cpx<T>* __restrict__ u, const cpx<T>* __restrict__ src, const cpx<T>* __restrict__ w, int N,
+                              long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  u[i] = cmul(src[i], w[i % N]);
+}
+
+// First-order coherence between two transformed copies of a 1-D ensemble (test/windowed_ft.jl:38-46):
+//   gram[k][l] = sum_t X1_t[k] conj(X2_t[l]),   written to out[i][j] (re, im), i = (k + N/2) % N, j = (l + N/2) % N,
+//   with the sign (-1)^(k+l): fft(fftshift(x))[k] = (-1)^k fft(x)[k] and ifftshift is that index shift (N even).
+template <typename T>
+__global__ void g1_kernel(const cpx<T>* __restrict__ x1, const cpx<T>* __restrict__ x2, double* __restrict__ out, int N,
+                          long long nbatch) {
+  __shared__ double Ar[16][17], Ai[16][17], Br[16][17], Bi[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int k0 = blockIdx.y * 16, l0 = blockIdx.x * 16;
+  const long long per = (nbatch + gridDim.z - 1) / gridDim.z;
+  const long long t0 = (long long)blockIdx.z * per, t1 = t0 + per < nbatch ? t0 + per : nbatch;
+  double accr = 0, acci = 0;
+  for (long long tb = t0; tb < t1; tb += 16) {
+    const long long t = tb + ty;
+    cpx<T> a = mk<T>((T)0, (T)0), b = mk<T>((T)0, (T)0);
+    if (t < t1) {
+      if (k0 + tx < N) a = x1[t * N + k0 + tx];
+      if (l0 + tx < N) b = x2[t * N + l0 + tx];
+    }
+    Ar[ty][tx] = (double)a.x;
+    Ai[ty][tx] = (double)a.y;
+    Br[ty][tx] = (double)b.x;
+    Bi[ty][tx] = (double)b.y;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {  // a * conj(b)
+      accr += Ar[q][ty] * Br[q][tx] + Ai[q][ty] * Bi[q][tx];
+      acci += Ai[q][ty] * Br[q][tx] - Ar[q][ty] * Bi[q][tx];
+    }
+    __syncthreads();
+  }
+  const int k = k0 + ty, l = l0 + tx;
+  if (k < N && l < N) {
+    const double sg = ((k + l) & 1) ? -1.0 : 1.0;
+    const size_t o = ((size_t)((k + N / 2) % N) * N + (size_t)((l + N / 2) % N)) * 2;
+    atomicAdd(out + o, sg * accr);
+    atomicAdd(out + o + 1, sg * acci);
+  }
+}
+
 // Cross-GPU barrier of the slab decomposition (one CTA, lane q talks to rank q): publish this rank's epoch in
 // every peer's flag array (a release store at system scope; the peer stores of the preceding kernel are complete
 // at its end), then wait until every peer has published the same epoch in ours.  Bounded spin: a rank that died
@@ -250,6 +299,7 @@ struct PlanBase {
   virtual int get_state(void* const* u) = 0;
   virtual int step(int64_t nsteps, const double* amp, const void* const* noise) = 0;
   virtual int observe(int kind, double* out) = 0;
+  virtual int observe_windowed(const double* w1, const double* w2, double* out) = 0;
   virtual void* state_ptr(int c) = 0;
   virtual int ipc_export(void* blob) = 0;
   virtual int ipc_attach(const void* blobs) = 0;
@@ -339,6 +389,9 @@ struct PlanT : PlanBase {
   size_t hs_cap = 0;
   void* xi_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   double* obs_dev = nullptr;
+  double* g1_dev = nullptr;  // M * N * N complex doubles (ggp_observe_windowed)
+  cpx<T>* win_dev = nullptr;
+  cpx<T>* xbuf1 = nullptr;
   double* g2_dev = nullptr;  // M * N * N doubles, allocated on first use (GGP_OBS_G2_MOMENTUM)
   cpx<T>* scratch[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
@@ -1300,6 +1353,71 @@ struct PlanT : PlanBase {
     return 0;
   }
 
+  // g1[i][j] = sum_traj conj(F2[j]) F1[i],  F_a = ifftshift(fft(fftshift(u .* w_a)))  (test/windowed_ft.jl:31-49), per
+  // component; the caller divides by length(sol).  1-D ensembles, even N.
+  int observe_windowed(const double* w1, const double* w2, double* out) override {
+    if (ndim != 1 || slab) return fail(GGP_ERR_UNSUPPORTED, "windowed correlations are defined for 1-D ensembles");
+    if (!size_supported(n[0]) || n[0] < 2) return fail(GGP_ERR_UNSUPPORTED, "windowed correlations need a power-of-two axis");
+    const int N = (int)n[0];
+    const long long total = nspatial * nbatch;
+    const size_t bytes = sizeof(cpx<T>) * (size_t)total;
+    int rc;
+    const size_t cnt = (size_t)M * N * N * 2;
+    if (!g1_dev && (rc = dalloc((void**)&g1_dev, sizeof(double) * cnt))) return rc;
+    if (!win_dev && (rc = dalloc((void**)&win_dev, sizeof(cpx<T>) * 2 * (size_t)N))) return rc;
+    if (!xbuf1 && (rc = dalloc((void**)&xbuf1, bytes))) return rc;
+    std::vector<cpx<T>> hw(2 * (size_t)N);
+    for (int k = 0; k < N; ++k) {
+      hw[(size_t)k] = mk<T>((T)w1[2 * k], (T)w1[2 * k + 1]);
+      hw[(size_t)N + k] = mk<T>((T)w2[2 * k], (T)w2[2 * k + 1]);
+    }
+    GGP_CUDA(cudaMemcpyAsync(win_dev, hw.data(), sizeof(cpx<T>) * hw.size(), cudaMemcpyHostToDevice, stream));
+    GGP_CUDA(cudaMemsetAsync(g1_dev, 0, sizeof(double) * cnt, stream));
+    HalfStep<T> none;
+    memset(&none, 0, sizeof(none));
+    for (int c = 0; c < M; ++c) {
+      if (!scratch[c] && (rc = dalloc((void**)&scratch[c], bytes))) return rc;
+      GGP_CUDA(cudaMemcpyAsync(scratch[c], u[c], bytes, cudaMemcpyDeviceToDevice, stream));
+    }
+    const unsigned wb = (unsigned)((total + 255) / 256);
+    const unsigned tiles = (unsigned)((N + 15) / 16);
+    unsigned zs = (unsigned)std::min<long long>(64, (nbatch + 255) / 256);
+    if (zs < 1) zs = 1;
+    // both windowed transforms of every component with the step's own FFT kernel (all components at once)
+    for (int a = 0; a < 2; ++a) {
+      for (int c = 0; c < M; ++c)
+        window_kernel<T><<<wb, 256, 0, stream>>>(u[c], scratch[c], win_dev + (size_t)a * N, N, total);
+      launches += M;
+      if ((rc = run_row(false, true, none, none))) return rc;
+      if (a == 0) {
+        // keep X1 of component 0; a second component's X1 is recomputed below (M = 2 is rare here)
+        GGP_CUDA(cudaMemcpyAsync(xbuf1, u[0], bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+    }
+    g1_kernel<T><<<dim3(tiles, tiles, zs), dim3(16, 16), 0, stream>>>(xbuf1, u[0], g1_dev, N, nbatch);
+    ++launches;
+    if (M == 2) {
+      GGP_CUDA(cudaMemcpyAsync(xbuf1, u[1], bytes, cudaMemcpyDeviceToDevice, stream));  // X2 of component 1
+      window_kernel<T><<<wb, 256, 0, stream>>>(u[1], scratch[1], win_dev, N, total);
+      window_kernel<T><<<wb, 256, 0, stream>>>(u[0], scratch[0], win_dev, N, total);
+      launches += 2;
+      if ((rc = run_row(false, true, none, none))) return rc;                            // X1 of component 1 in u[1]
+      g1_kernel<T><<<dim3(tiles, tiles, zs), dim3(16, 16), 0, stream>>>(u[1], xbuf1, g1_dev + (size_t)N * N * 2, N, nbatch);
+      ++launches;
+    }
+    for (int c = 0; c < M; ++c) GGP_CUDA(cudaMemcpyAsync(u[c], scratch[c], bytes, cudaMemcpyDeviceToDevice, stream));
+    GGP_CUDA(cudaGetLastError());
+#ifdef GGP_WITH_NCCL
+    if (comm && nranks > 1) {
+      ncclResult_t r = ncclAllReduce(g1_dev, g1_dev, cnt, ncclDouble, ncclSum, comm, stream);
+      if (r != ncclSuccess) return fail(GGP_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+#endif
+    GGP_CUDA(cudaMemcpyAsync(out, g1_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream));
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
   int observe(int kind, double* out) override {
     const int threads = 256;
     const unsigned blocks = (unsigned)((nspatial + threads - 1) / threads);
@@ -1499,6 +1617,12 @@ int ggp_observe(ggp_plan* p, int kind, double* out) {
   GGP_ENTER(p);
   if (!out) return fail(GGP_ERR_INVALID, "null output");
   return p->impl->observe(kind, out);
+}
+
+int ggp_observe_windowed(ggp_plan* p, const double* w1, const double* w2, double* out) {
+  GGP_ENTER(p);
+  if (!w1 || !w2 || !out) return fail(GGP_ERR_INVALID, "null argument");
+  return p->impl->observe_windowed(w1, w2, out);
 }
 
 int ggp_comm_unique_id(void* id) {

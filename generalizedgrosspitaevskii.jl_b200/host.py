@@ -793,6 +793,16 @@ class StrangSplittingIterator:
         L.check(self.lib.ggp_checkpoint_load(self.handle, buf.ctypes.data, n))
         self._step_index = int(np.frombuffer(buf[n:].tobytes(), dtype=np.int64)[0])
 
+    def observe_windowed(self, w1, w2):
+        """sum_traj conj(F2[j]) F1[i], F_a = ifftshift(fft(fftshift(u .* w_a)))  (test/windowed_ft.jl:31-49, before its
+        division by length(sol)), per component, computed on the device: complex array (M, N, N)."""
+        N = self.u[0].shape[-1]
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(w1, dtype=np.complex128), (N,)))
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(w2, dtype=np.complex128), (N,)))
+        out = np.empty((self.M, N, N), dtype=np.complex128)
+        L.check(self.lib.ggp_observe_windowed(self.handle, a.ctypes.data, b.ctypes.data, out.ctypes.data))
+        return out
+
     def observe(self, kind):
         shape = self.u[0].shape[self.u[0].ndim - self.prob.ndim:]
         nspatial = int(np.prod(shape))

@@ -105,6 +105,17 @@ function ggp_observe!(out::Array{Float64}, h::Ptr{Cvoid}, kind::Cint)
     out
 end
 
+# Windowed first-order coherence (test/windowed_ft.jl:31-49 `correlation`, before its division by length(sol)):
+# w1, w2 = window values on the direct grid; returns an N×N×M ComplexF64 array laid out [j, i, c] in Julia's
+# column-major order (the C side writes out[c][i][j]).
+function ggp_observe_windowed(h::Ptr{Cvoid}, w1::Vector{ComplexF64}, w2::Vector{ComplexF64}, M::Integer)
+    N = length(w1)
+    out = Array{ComplexF64}(undef, N, N, M)
+    GC.@preserve w1 w2 out _check(ccall(_sym(:ggp_observe_windowed), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        h, Ptr{Float64}(pointer(w1)), Ptr{Float64}(pointer(w2)), Ptr{Float64}(pointer(out))))
+    out
+end
+
 # Checkpoint / resume (include/ggp.h): fields + Philox counter word + F_now amplitude as one byte vector
 function ggp_checkpoint(h::Ptr{Cvoid})
     n = ccall(_sym(:ggp_checkpoint_bytes), Int64, (Ptr{Cvoid},), h)

@@ -215,6 +215,13 @@ int ggp_checkpoint_load(ggp_plan *plan, const void *blob, uint64_t size);
    If a communicator was attached with ggp_comm_init the sums are all-reduced over ranks (NCCL). */
 int ggp_observe(ggp_plan *plan, int kind, double *out_host);
 
+/* Windowed first-order coherence of a 1-D ensemble (test/windowed_ft.jl:31-49, `correlation`) without downloading
+   the ensemble:  out[c][i][j] (re, im) = sum over local trajectories conj(F2[j]) * F1[i],
+   F_a = ifftshift(fft(fftshift(u_c .* w_a)))  for the two windows w1, w2 (N complex doubles each, values on the
+   direct grid).  The caller divides by length(sol) = N * ntraj.  All-reduced over ranks like ggp_observe.
+   out_host: ncomp * N * N complex doubles. */
+int ggp_observe_windowed(ggp_plan *plan, const double *w1, const double *w2, double *out_host);
+
 /* Multi-GPU (one process per GPU).  unique_id: the 128-byte ncclUniqueId produced by
    ggp_comm_unique_id on rank 0 and broadcast by the caller's own plumbing. */
 int ggp_comm_unique_id(void *unique_id_128);

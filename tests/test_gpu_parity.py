@@ -379,3 +379,25 @@ def test_g2_momentum_observable(G, ntraj, N, dtype):
         for n in range(N):
             G2_ref[m, n] = np.mean(inten[:, m] * inten[:, n] - (1 + (m == n)) * cm / 2 * (inten[:, m] + inten[:, n] - cm / 2))
     assert np.allclose(G2_dev, G2_ref, rtol=1e3 * tol, atol=1e3 * tol * np.abs(G2_ref).max())
+
+
+@pytest.mark.parametrize("M,ntraj,N", [(1, 300, 64), (2, 33, 32)])
+def test_windowed_correlation_observable(G, M, ntraj, N):
+    """`correlation` of test/windowed_ft.jl:31-49 on the device (ggp_observe_windowed) against the
+    host restatement used by the known-answer tests, on the same ensemble."""
+    from test_oracle_known_answers import _window, windowed_correlation
+    rng = np.random.default_rng(5)
+    L = 20.0
+    u0 = tuple((rng.standard_normal((ntraj, N)) + 1j * rng.standard_normal((ntraj, N))) for _ in range(M))
+    prob = G.GrossPitaevskiiProblem(u0, (L,), dispersion=lambda ks, p: ks[0] ** 2 / 2)
+    it = G.init(prob, G.StrangSplitting(), (0, 1.0), dt=0.1, nsaves=1, save_start=False)
+    it.advance(3)
+    state = [np.array(x) for x in it.fetch()]
+    rs = -L / 2 + np.arange(N) * (L / N)
+    for par1, par2 in (((-1, 3), (1, 3)), ((0, 5), (0, 4))):
+        got = it.observe_windowed(_window(rs, par1), _window(rs, par2))
+        for c in range(M):
+            ref = windowed_correlation(state[c], rs, par1, par2) * state[c].size
+            assert np.allclose(got[c], ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max()), (c, par1, par2)
+    assert all(np.array_equal(a, b) for a, b in zip(state, it.fetch()))       # the state is untouched
+    it.close()
