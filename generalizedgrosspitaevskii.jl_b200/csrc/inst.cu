@@ -21,16 +21,29 @@ static int set_smem(KernelT k, size_t bytes) {
   return 0;
 }
 
-// Launch with programmatic stream serialization (see pdl_wait() in cplx.cuh) when the grid is at least about
-// one full wave of the GPU: the next kernel's CTAs then slip into the SM slots this grid frees while it
-// drains (measured on C2 chained: 63.7 -> 61.8 us/step; 4096^2: 313.9 -> 308.2).  For grids below one wave it is
-// counter-productive (1024^2: 24.7 -> 29.8 us/step: the early CTAs land wherever a slot frees first and
-// unbalance the SMs), so those launch the plain way.  GGP_NO_PDL=1 / GGP_PDL=1 force it off / on.
+// Launch with programmatic stream serialization (see pdl_wait() in cplx.cuh): the next kernel's CTAs are scheduled
+// while this grid is still running, with their parameters, index arithmetic and table staging done, and block in
+// griddepcontrol.wait until this grid has completed.  WHERE a grid lets its dependent go matters:
+//  * grids of at least one wave trigger at their very start (pdl_pos 0): the dependent's CTAs slip into the SM slots
+//    this grid frees while it drains (C2 chained 63.7 -> 61.8 us/step, 4096^2 313.9 -> 308.2);
+//  * grids below one wave trigger right before their final stores (pdl_pos 3): triggered at the start, the dependent's
+//    CTAs land next to this grid's on whatever SM has room and unbalance it (1024^2 chained 22.5 -> 26.7 us/step);
+//    triggered late, only the launch latency and the prologue overlap this grid's tail: 1024^2 22.5 -> 17.9 us/step,
+//    512^2 14.4 -> 10.5 (profiles/r01_notes.md, session 4).
+// GGP_NO_PDL=1 switches it off, GGP_PDL_POS=0..3 forces a trigger position.  Kernels without a pdl_pos parameter
+// (oned_kernel) keep the old rule: programmatic launch only for grids of at least one wave.
+static bool pdl_small_grid(unsigned grid, unsigned block) { return (unsigned long long)grid * block < 148ull * 1024ull; }
+static int pdl_pos_for(unsigned grid, unsigned block) {
+  static const int v = getenv("GGP_PDL_POS") ? atoi(getenv("GGP_PDL_POS")) : -1;
+  if (v >= 0) return v > 3 ? 3 : v;
+  return pdl_small_grid(grid, block) ? 3 : 0;
+}
+
 template <typename P>
 static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const P& p,
-                      unsigned cluster = 1) {
+                      unsigned cluster = 1, bool has_pos = false) {
   static const int mode = getenv("GGP_NO_PDL") ? 0 : (getenv("GGP_PDL") ? 2 : 1);
-  const bool pdl = mode == 2 || (mode == 1 && (unsigned long long)grid * block >= 148ull * 1024ull);
+  const bool pdl = mode == 2 || (mode == 1 && (has_pos || !pdl_small_grid(grid, block)));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
@@ -65,7 +78,9 @@ static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   auto k = row_kernel<T, N, M, PWV>;
   int e = set_smem(k, smem);
   if (e) return e;
-  return launch_pdl<RowParams<T>>(k, grid, K::ROW_THREADS, smem, st, p);
+  RowParams<T> q = p;
+  q.pdl_pos = pdl_pos_for(grid, K::ROW_THREADS);
+  return launch_pdl<RowParams<T>>(k, grid, K::ROW_THREADS, smem, st, q, 1, true);
 }
 
 template <typename T, int N, int M>
@@ -204,8 +219,9 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   auto k = str_kernel<T, N, M>;
   int e = set_smem(k, smem);
   if (e) return e;
+  p.pdl_pos = pdl_pos_for((unsigned)grid, (unsigned)(W * K::TPL));
   static const unsigned cl = getenv("GGP_STR_CLUSTER") ? (unsigned)atoi(getenv("GGP_STR_CLUSTER")) : 1u;
-  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p, cl);
+  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p, cl, true);
 }
 
 template <typename T, int N>

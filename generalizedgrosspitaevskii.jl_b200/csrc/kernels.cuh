@@ -40,6 +40,8 @@ struct RowParams {
   PointwiseParams<T> pw;
   HalfStep<T> hs[2];  // trailing half-step of step n, leading half-step of step n+1
   int flags;          // bit 0: inverse FFT_x first, bit 1: forward FFT_x last
+  int pdl_pos;        // where this grid lets its dependent launch: 0 at its start, 1 after its loads, 2 after the
+                      // half-steps / exp_D multiply, 3 before its final stores (see launch_pdl in inst.cu)
   const void* tw2;    // twiddles of the packed two-line kernels (packed.cuh), fp32 plans only
 };
 
@@ -70,6 +72,7 @@ struct alignas(64) StrParams {
   long long dst_ls, dst_s1, dst_s2, dst_base;
   int scatter, dst_shift;
   int dl_smem;  // KIND_SEP: D_line is staged in shared memory behind the exchange lines (set by the launcher)
+  int pdl_pos;  // as RowParams::pdl_pos
   int slab;     // slab-decomposed plan (LDG loads, peer stores): the launcher picks 128-byte tiles
   int pf_dist;  // > 0: while waiting for its own tile a CTA prefetches tile (blockIdx + pf_dist) into L2 -- set by the
                 // launcher to the number of resident CTAs when the state does not fit the L2 (see str_kernel)
@@ -317,6 +320,7 @@ __device__ __forceinline__ void row_parked_body(const RowParams<T>& p, cpx<T>* s
       }
     }
   }
+  if (p.pdl_pos == 1) pdl_launch_dependents();
   if (active) {
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -332,6 +336,7 @@ __device__ __forceinline__ void row_parked_body(const RowParams<T>& p, cpx<T>* s
       a[m] = f[1];
     }
   }
+  if (p.pdl_pos >= 2) pdl_launch_dependents();
 #pragma unroll 1
   for (int c = 1; c >= 0; --c) {
     if (c == 0) {
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
   const long long soff = (line % p.lines_per_image) * N + t;
   cpx<T>* sl = smem + (size_t)grp * M * LS;
 
-  pdl_launch_dependents();
+  if (p.pdl_pos == 0) pdl_launch_dependents();
   pdl_wait();
   if constexpr (K::row_parked(M, PWV)) {
     row_parked_body<T, N, PWV>(p, sl, t, active, goff, soff);
@@ -375,12 +380,15 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
     for (int c = 0; c < M; ++c)
 #pragma unroll
       for (int m = 0; m < E; ++m) v[c][m] = active ? p.u[c][goff + m * TPL] : mk<T>((T)0, (T)0);
+    if (p.pdl_pos == 1) pdl_launch_dependents();
 
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
       if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 0);
       if (it == 0 && active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 2, soff, goff, TPL);
+      if (it == 0 && p.pdl_pos == 2) pdl_launch_dependents();
     }
+    if (p.pdl_pos == 3) pdl_launch_dependents();
     if (active) {
 #pragma unroll
       for (int c = 0; c < M; ++c)
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
       dperp = p.D[0][toff - (long long)t * p.ls];
     }
   }
-  pdl_launch_dependents();
+  if (p.pdl_pos == 0) pdl_launch_dependents();
   pdl_wait();
   cpx<T> v[M][E];
   if (p.tma) {
@@ -503,10 +511,12 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   }
   if (tws || (sep && p.dl_smem)) asm volatile("cp.async.wait_all;" ::: "memory");  // published by the barriers of the transform
 
+  if (p.pdl_pos == 1) pdl_launch_dependents();
   const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
 #pragma unroll 1
   for (int it = it0; it <= it1; ++it) {
     fft_fwd_all<T, N, M, SyncBlock, K::FACT>(v, t, sl, p.LS, twp, it == 1, twc);
+    if (it == it0 && p.pdl_pos == 2) pdl_launch_dependents();
     if (it == 0 && p.mode == 1) {
       if (p.dkind == KIND_SEP) {
         if constexpr (TwT<T>::split) {
@@ -550,6 +560,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
       }
     }
   }
+  if (p.pdl_pos == 3) pdl_launch_dependents();
   if (p.scatter) {
     const long long dbase = p.dst_base + xt * p.W + xw + o1 * p.dst_s1 + o2 * p.dst_s2;
     const int mask = (1 << p.dst_shift) - 1;
