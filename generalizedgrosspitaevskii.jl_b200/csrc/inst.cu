@@ -2,6 +2,7 @@
 // library builds in parallel.  Compiled with -DGGP_T=float|double -DGGP_N=<line length>.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "kernels.cuh"
 #ifdef GGP_TMA
 #include "str_tma.cuh"
@@ -26,24 +27,56 @@ static int set_smem(KernelT k, size_t bytes) {
 // griddepcontrol.wait until this grid has completed.  WHERE a grid lets its dependent go matters:
 //  * grids of at least one wave trigger at their very start (pdl_pos 0): the dependent's CTAs slip into the SM slots
 //    this grid frees while it drains (C2 chained 63.7 -> 61.8 us/step, 4096^2 313.9 -> 308.2);
-//  * grids below one wave trigger right before their final stores (pdl_pos 3): triggered at the start, the dependent's
+//  * grids below one wave (fewer CTAs than SM slots, by the occupancy calculator) trigger right before their final
+//    stores (pdl_pos 3): triggered at the start, the dependent's
 //    CTAs land next to this grid's on whatever SM has room and unbalance it (1024^2 chained 22.5 -> 26.7 us/step);
 //    triggered late, only the launch latency and the prologue overlap this grid's tail: 1024^2 22.5 -> 17.9 us/step,
 //    512^2 14.4 -> 10.5 (profiles/r01_notes.md, session 4).
+//  * in between (more than one wave, but fewer than 148 x 1024 threads, e.g. C3's register-heavy kernels): plain launch,
+//    either trigger position measured slower (C3 125.8 -> 131.3 us/step with pos 3).
 // GGP_NO_PDL=1 switches it off, GGP_PDL_POS=0..3 forces a trigger position.  Kernels without a pdl_pos parameter
 // (oned_kernel) keep the old rule: programmatic launch only for grids of at least one wave.
 static bool pdl_small_grid(unsigned grid, unsigned block) { return (unsigned long long)grid * block < 148ull * 1024ull; }
-static int pdl_pos_for(unsigned grid, unsigned block) {
+// the whole grid is resident at once (fewer CTAs than SM slots for this kernel, block size and shared memory)
+template <typename KernelT>
+static bool pdl_below_one_wave(KernelT k, unsigned grid, unsigned block, size_t smem) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  // one occupancy query per (kernel, block size, shared memory) and host thread, not per launch
+  struct Entry { const void* k; unsigned block; size_t smem; int per_sm; };
+  thread_local std::vector<Entry> cache;
+  int per_sm = -1;
+  for (const Entry& e : cache)
+    if (e.k == (const void*)k && e.block == block && e.smem == smem) per_sm = e.per_sm;
+  if (per_sm < 0) {
+    per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (int)block, smem) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 0;
+    }
+    cache.push_back(Entry{(const void*)k, block, smem, per_sm});
+  }
+  if (per_sm < 1) return false;
+  return (unsigned long long)grid <= (unsigned long long)per_sm * (unsigned)sms;
+}
+// trigger position and whether to use the programmatic launch at all, for kernels with a pdl_pos parameter
+static int pdl_pos_for(bool below_one_wave, unsigned grid, unsigned block, bool* use) {
   static const int v = getenv("GGP_PDL_POS") ? atoi(getenv("GGP_PDL_POS")) : -1;
+  *use = below_one_wave || !pdl_small_grid(grid, block);   // in between (a few waves of few threads): plain launch, as measured
   if (v >= 0) return v > 3 ? 3 : v;
-  return pdl_small_grid(grid, block) ? 3 : 0;
+  return below_one_wave ? 3 : 0;
 }
 
 template <typename P>
 static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const P& p,
                       unsigned cluster = 1, bool has_pos = false) {
   static const int mode = getenv("GGP_NO_PDL") ? 0 : (getenv("GGP_PDL") ? 2 : 1);
-  const bool pdl = mode == 2 || (mode == 1 && (has_pos || !pdl_small_grid(grid, block)));
+  const bool pdl = mode == 2 || (mode == 1 && (has_pos || !pdl_small_grid(grid, block)));  // has_pos: the caller decided
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
@@ -79,8 +112,9 @@ static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   int e = set_smem(k, smem);
   if (e) return e;
   RowParams<T> q = p;
-  q.pdl_pos = pdl_pos_for(grid, K::ROW_THREADS);
-  return launch_pdl<RowParams<T>>(k, grid, K::ROW_THREADS, smem, st, q, 1, true);
+  bool use = false;
+  q.pdl_pos = pdl_pos_for(pdl_below_one_wave(k, grid, K::ROW_THREADS, smem), grid, K::ROW_THREADS, &use);
+  return launch_pdl<RowParams<T>>(k, grid, K::ROW_THREADS, smem, st, q, 1, use);
 }
 
 template <typename T, int N, int M>
@@ -219,9 +253,11 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   auto k = str_kernel<T, N, M>;
   int e = set_smem(k, smem);
   if (e) return e;
-  p.pdl_pos = pdl_pos_for((unsigned)grid, (unsigned)(W * K::TPL));
+  bool use = false;
+  p.pdl_pos = pdl_pos_for(pdl_below_one_wave(k, (unsigned)grid, (unsigned)(W * K::TPL), smem), (unsigned)grid,
+                          (unsigned)(W * K::TPL), &use);
   static const unsigned cl = getenv("GGP_STR_CLUSTER") ? (unsigned)atoi(getenv("GGP_STR_CLUSTER")) : 1u;
-  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p, cl, true);
+  return launch_pdl<StrParams<T>>(k, (unsigned)grid, (unsigned)(W * K::TPL), smem, st, p, cl, use);
 }
 
 template <typename T, int N>
