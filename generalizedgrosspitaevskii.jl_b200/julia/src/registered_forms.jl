@@ -10,7 +10,7 @@ _aslist(x::SMatrix{1,1}, M) = (ntuple(_ -> ComplexF64(x[1]), M), false)
 function recognise_nonlinearity(f, param, ::Val{M}) where {M}
     rng = Random.Xoshiro(0xC0FFEE)
     P = 4 * (M + 1) + 8
-    probe() = SVector{M,ComplexF64}(ntuple(_ -> (0.2 + 1.8rand(rng)) * cis(2π * rand(rng)), M))
+    probe() = SVector{M,ComplexF64}(ntuple(_ -> (0.2 + 1.8 * rand(rng)) * cis(2π * rand(rng)), M))
     us = [probe() for _ in 1:P]
     vals = [_aslist(f(u, param), M) for u in us]
     scalar = vals[1][2]
@@ -88,12 +88,12 @@ function recognise_noise(f, prob)
     inbounds = all(g -> length(g) ≥ n1, rs)
     pts = inbounds ? [map(g -> g[k], rs) for k in 1:n1] : nothing
     ev(u, r) = ComplexF64.(collect(_aslist(f(SVector{M,ComplexF64}(u), r, prob.param), M)[1]))
-    probe() = ntuple(_ -> (0.2 + 1.8rand(rng)) * cis(2π * rand(rng)), M)
+    probe() = ntuple(_ -> (0.2 + 1.8 * rand(rng)) * cis(2π * rand(rng)), M)
     uref = probe()
     along = pts === nothing ? nothing : [ev(uref, r) for r in pts]
     k0 = along === nothing ? 0 : argmax(map(v -> maximum(abs, v), along))
     r0 = along === nothing ? map(g -> g[cld(length(g), 2)], rs) : pts[k0]
-    U = [probe() for _ in 1:(4(M + 1) + 8)]
+    U = [probe() for _ in 1:(4 * (M + 1) + 8)]
     A = [j == 0 ? 1.0 : abs(u[j]) for u in U, j in 0:M]
     Y = permutedims(reduce(hcat, [ev(u, r0) for u in U]))
     coef = A \ Y                                                  # (M+1) × M
@@ -101,20 +101,20 @@ function recognise_noise(f, prob)
     pred = [j == 0 ? 1.0 : abs(u[j]) for u in V, j in 0:M] * coef
     truth = permutedims(reduce(hcat, [ev(u, r0) for u in V]))
     scale = max(maximum(abs, truth), maximum(abs, coef), floatmin(Float64))
-    maximum(abs, pred .- truth) ≤ 1e-9scale ||
+    maximum(abs, pred .- truth) ≤ 1e-9 * scale ||
         error("noise amplitude is not of the registered form P(r)·(e_i + Σ_j a_ij |u_j|) (no CPU fallback)")
-    coef[abs.(coef) .< 1e-13scale] .= 0
+    coef[abs.(coef) .< 1e-13 * scale] .= 0
     e, a = coef[1, :], permutedims(coef[2:end, :])                 # a[i, j]
     P = nothing
     if pts === nothing
-        maximum(abs, ev(uref, map(first, rs)) .- ev(uref, r0)) ≤ 1e-12scale ||
+        maximum(abs, ev(uref, map(first, rs)) .- ev(uref, r0)) ≤ 1e-12 * scale ||
             error("position-dependent noise with n₁ longer than another axis: the reference's `point` is out of bounds")
     else
         ref = along[k0]; c = argmax(abs.(ref))
         if abs(ref[c]) > 0
             prof = ComplexF64[v[c] / ref[c] for v in along]
             if maximum(abs, prof .- 1) > 1e-12
-                all(k -> maximum(abs, along[k] .- prof[k] .* ref) ≤ 1e-9scale, 1:n1) ||
+                all(k -> maximum(abs, along[k] .- prof[k] .* ref) ≤ 1e-9 * scale, 1:n1) ||
                     error("noise amplitude does not separate as P(r) × (field part)")
                 P = prof
             end
@@ -145,5 +145,5 @@ function separable_dispersion_tol(D, rg, param, table::AbstractArray{<:Number})
     tab = reshape(ComplexF64.(table), :, size(table, d))          # (perp, line): the strided kernel runs along the last axis
     d0 = tab[1, 1]; (d0 == 0 || !isfinite(d0)) && return 0.0
     dev = maximum(abs, tab .- tab[:, 1] .* permutedims(tab[1, :]) ./ d0)
-    1.25dev / maximum(abs, tab) + 1e-9
+    1.25 * dev / maximum(abs, tab) + 1e-9
 end
