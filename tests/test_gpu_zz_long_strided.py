@@ -1,8 +1,7 @@
 """Strided axes of 4096 and 8192 points against the oracle: the geometries only the large-grid benchmarks use
 (factorised twiddles `w_N^j = A[j>>6] B[j&63]`, 256 / 512 threads per line, 16-byte tiles) on grids small enough for the
 CPU oracle -- a long strided axis next to a short contiguous one.  Separable dispersion (two-factor exp_D with D_line
-staged in shared memory) and a coupled one (full table).  Sorted last on purpose: these kernels were added at the
-end of round 1 after the GPU budget of the round was spent on the measurements."""
+staged in shared memory) and a coupled one (full table)."""
 import numpy as np
 import pytest
 
