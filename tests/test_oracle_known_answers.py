@@ -228,3 +228,20 @@ def test_noise_point_quirk_q2():
     src = lambda shape, dtype: (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dtype)
     O.solve(prob, O.StrangSplitting(), (0, 0.1), dt=0.05, nsaves=1, noise_source=src)
     assert seen and all(s == [(1, 8), (1, 8)] for s in seen)
+
+
+def test_field_dependent_noise_uses_pre_update_field():
+    """kernels.jl:40-49: `fields` is read once, before the update; the noise amplitude eta(fields, point, param) and the
+    nonlinear phase are both evaluated on it:  result = cis(-dt G(u)) u - i sqrt(dt) eta(u) xi."""
+    rng = np.random.default_rng(2)
+    u = (rng.standard_normal((3, 8)) + 1j * rng.standard_normal((3, 8)))
+    xi = (rng.standard_normal((3, 8)) + 1j * rng.standard_normal((3, 8)))
+    g, alpha, c, dt = 0.7, 0.3, 0.2, 0.05
+    out = O.muladd([u], O.multiplicativeIdentity, O.additiveIdentity, O.additiveIdentity, dt,
+                   lambda f, p: g * O.abs2(f[0]), lambda f, r, p: c + alpha * abs(f[0]), [xi], None,
+                   (np.zeros((1, 8)),))
+    want = np.exp(-1j * dt * g * np.abs(u) ** 2) * u - 1j * np.sqrt(dt) * (c + alpha * np.abs(u)) * xi
+    assert np.allclose(out[0], want, rtol=1e-14, atol=1e-15)
+    post = np.exp(-1j * dt * g * np.abs(u) ** 2) * u
+    wrong = post - 1j * np.sqrt(dt) * (c + alpha * np.abs(post + 0.1)) * xi          # any post-update evaluation differs
+    assert not np.allclose(out[0], wrong)
