@@ -1,6 +1,7 @@
-"""3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2 GPUs, compared with the unsharded CPU
-oracle -- once with the transposes fused into the FFT kernels as peer stores over NVLink (CUDA IPC, the
-default), once with the ncclSend/ncclRecv transposes.  Needs >= 2 CUDA devices (gpurun --gpus 2)."""
+"""3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2, 4 and 8 GPUs, compared with the unsharded
+CPU oracle -- once with the transposes fused into the FFT kernels as peer stores over NVLink (CUDA IPC, the
+default), once with the ncclSend/ncclRecv transposes.  Every world size exercises its own scatter index math
+(`dst_shift`, `dst_base` of StrParams).  Needs >= `world` CUDA devices (gpurun --gpus N); smaller boxes skip."""
 import os
 import sys
 
@@ -74,16 +75,17 @@ def _worker(rank, world, port, q, p2p):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("p2p", [True, False], ids=["peer_stores", "nccl"])
-def test_slab_decomposition_matches_oracle(p2p):
+def test_slab_decomposition_matches_oracle(p2p, world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ggp_oracle as O
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300) + (301 if p2p else 0)
+    port = 29600 + (os.getpid() % 300) + (301 if p2p else 0) + 7 * world
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()

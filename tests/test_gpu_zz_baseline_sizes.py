@@ -1,0 +1,141 @@
+"""CUDA path vs the CPU oracle AT the BASELINE sizes: the exact kernel instantiations the
+benchmarks time -- `row_kernel<float,2048,1,KERR>` + `str_kernel<float,2048,1>` with the TMA tile path and the staged
+D_line (C2), the two-component fp64 kernels at 1024 (C3), the 3-D chain at 256^3 (C5), the stochastic fp64 row kernel
+at 256^2 (C4, host-fed noise) -- and every long CONTIGUOUS line of the 2-D row kernel (1024 ... 8192), which the 1-D
+line-length test does not reach (it runs `oned_kernel`).  Norm conservation / time reversal (test_gpu_parity.py) are
+blind to unitary, reversible index errors; these comparisons are not.
+
+Oracle cost on the GPU box's host cores: ~1 min in total (scipy.fft on all cores for the big grids).
+Tolerances are BASELINE.json's: relative L2 <= 1e-10 (ComplexF64), <= 1e-4 (ComplexF32).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ggp_oracle as O
+import problems as P
+
+pytestmark = pytest.mark.gpu
+TOL = {np.dtype(np.complex128): 1e-10, np.dtype(np.complex64): 1e-4}
+CORES = len(os.sched_getaffinity(0))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import ggp_b200
+    ggp_b200.load()
+    assert ggp_b200.lib.load().ggp_device_count() >= 1
+    return ggp_b200
+
+
+def rel_l2(a, b):
+    num = sum(np.linalg.norm((x.astype(np.complex128) - y.astype(np.complex128)).ravel()) ** 2 for x, y in zip(a, b))
+    den = sum(np.linalg.norm(y.astype(np.complex128).ravel()) ** 2 for y in b)
+    return float(np.sqrt(num / den))
+
+
+def solve_oracle(pb, **kw):
+    prob = O.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    return O.solve(prob, O.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"],
+                   save_start=pb.get("save_start", True), fft_workers=CORES, **kw)[1]
+
+
+def solve_gpu(G, pb, **kw):
+    prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+    return G.solve(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=pb["nsaves"],
+                   save_start=pb.get("save_start", True), **kw)[1]
+
+
+def test_c2_2048_c64_20_steps_three_way(G):
+    """BASELINE configs[1] at its own size: 2048^2 ComplexF32, 20 steps; ours vs fp32 oracle, ours vs fp64 oracle and
+    fp32 oracle vs fp64 oracle are printed together (SURVEY hard part 5)."""
+    g = solve_gpu(G, P.kerr2d(G, N=2048, dtype=np.complex64, nsteps=20))
+    o32 = solve_oracle(P.kerr2d(O, N=2048, dtype=np.complex64, nsteps=20))
+    o64 = solve_oracle(P.kerr2d(O, N=2048, dtype=np.complex128, nsteps=20))
+    d_g32, d_g64, d_3264 = rel_l2(g, o32), rel_l2(g, o64), rel_l2(o32, o64)
+    print(f"\nC2 2048^2 c64, 20 steps: ours-o32 {d_g32:.3e}  ours-o64 {d_g64:.3e}  o32-o64 {d_3264:.3e}")
+    assert d_g32 <= 1e-4 and d_g64 <= 1e-4
+    # the run is not a fixed point: the field moved by far more than the tolerance
+    assert rel_l2([o64[0][-1]], [o64[0][0]]) > 1e-2
+
+
+def test_c2_2048_c128_10_steps(G):
+    """The same kernels' fp64 instantiations at 2048^2 (1e-10 gate)."""
+    g = solve_gpu(G, P.kerr2d(G, N=2048, dtype=np.complex128, nsteps=10))
+    o = solve_oracle(P.kerr2d(O, N=2048, dtype=np.complex128, nsteps=10))
+    assert rel_l2(g, o) <= 1e-10
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_c3_1024_two_component_10_steps(G, dtype):
+    """BASELINE configs[2] at its own size: 1024^2, M = 2, 2x2 matrix-exponential dispersion table, SVector
+    nonlinearity, time-dependent separable pump; 10 steps (the pump is switched on from t = 0)."""
+    kw = dict(N=1024, nsaves=2, tspan=(0, 0.5), dt=0.05, time_pump=True, dtype=dtype)
+    g = solve_gpu(G, P.exciton_polariton(G, **kw))
+    o = solve_oracle(P.exciton_polariton(O, **kw))
+    assert np.abs(o[0][-1]).max() > 0
+    assert rel_l2(g, o) <= TOL[np.dtype(dtype)]
+
+
+def test_c5_256_cubed_4_steps(G):
+    """BASELINE configs[4]'s problem at 256^3 ComplexF32, one GPU (row + y forward + z FFT.D.iFFT + y inverse)."""
+    g = solve_gpu(G, P.kerr3d(G, N=256, dtype=np.complex64, nsteps=4))
+    o = solve_oracle(P.kerr3d(O, N=256, dtype=np.complex64, nsteps=4))
+    assert rel_l2(g, o) <= 1e-4
+
+
+def test_c4_256_squared_8_trajectories_host_noise(G):
+    """BASELINE configs[3]'s problem at its own grid (256^2 ComplexF64, `row_kernel<double,256,1,STOCH>`), 8
+    trajectories, 4 steps, fed the oracle's noise buffers (test mode): deterministic gate."""
+    kw = dict(ntraj=8, N=256, ndim=2, tspan=(0, 0.2), dt=0.05)
+    rng = np.random.default_rng(5)
+    rec = []
+
+    def noise_source(shape, dtype):
+        return ((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)).astype(dtype)
+
+    o = solve_oracle(P.truncated_wigner(O, **kw), noise_source=noise_source, record_noise=rec)
+    g = solve_gpu(G, P.truncated_wigner(G, **kw), noise_buffers=rec)
+    assert rel_l2(g, o) <= 1e-10
+
+
+def _rect_problem(ns, shape, dtype, lengths):
+    rng = np.random.default_rng(23)
+    real = np.float32 if dtype == np.complex64 else np.float64
+    n2, n1 = shape
+    y = np.arange(n2)[:, None] / n2
+    x = np.arange(n1)[None, :] / n1
+    env = np.exp(-30 * (x - 0.5) ** 2) * (1 + 0.3 * np.cos(2 * np.pi * y))
+    u0 = (env * (1 + 0.05 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)))).astype(dtype)
+
+    def dispersion(ks, p):
+        return (ks[0] * ks[0] + ks[1] * ks[1]) / 2
+
+    def nonlinearity(u, p):
+        return real(0.5) * ns.abs2(u[0])
+
+    return dict(u0=(u0,), lengths=tuple(real(v) for v in lengths),
+                kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity),
+                tspan=(real(0), real(0.004)), dt=real(0.001), nsaves=2)
+
+
+@pytest.mark.parametrize("n1", [1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_long_contiguous_lines_2d(G, dtype, n1):
+    """2-D `row_kernel` lines of 1024 ... 8192 points (512-thread lines and radix-16/32 schedules at 8192) next to a
+    short strided axis (16 rows), 4 steps."""
+    pbg, pbo = (_rect_problem(ns, (16, n1), dtype, (64.0, 2.0)) for ns in (G, O))
+    g, o = solve_gpu(G, pbg), solve_oracle(pbo)
+    assert rel_l2(g, o) <= TOL[np.dtype(dtype)]
+    assert rel_l2([o[0][-1]], [o[0][0]]) > 1e-4
+
+
+@pytest.mark.parametrize("n2", [1024, 2048])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_strided_lines_1024_2048(G, dtype, n2):
+    """`str_kernel<*,1024>` / `<*,2048>` (TMA tile path, twiddles and D_line in shared memory) on a 64-wide grid: every
+    thread-to-element mapping of the headline instantiation, checked point by point."""
+    pbg, pbo = (_rect_problem(ns, (n2, 64), dtype, (2.0, 64.0)) for ns in (G, O))
+    g, o = solve_gpu(G, pbg), solve_oracle(pbo)
+    assert rel_l2(g, o) <= TOL[np.dtype(dtype)]
