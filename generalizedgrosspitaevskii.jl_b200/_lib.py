@@ -9,11 +9,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggp.so")
 LIB_PATH = os.environ.get("GGP_LIBRARY", LIB_PATH)  # A/B measurements of kernel variants (tools/)
 
-GGP_ABI_VERSION = 3
+GGP_ABI_VERSION = 4
 GGP_C64, GGP_C128 = 0, 1
-TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL = 0, 1, 2, 3
+TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL, TABLE_SEP_AXES = 0, 1, 2, 3, 4
 NL_NONE, NL_DIAG = 0, 1
-PUMP_NONE, PUMP_SEPARABLE = 0, 1
+PUMP_NONE, PUMP_SEPARABLE, PUMP_DENSE = 0, 1, 2
 NOISE_NONE, NOISE_CONST, NOISE_FIELD = 0, 1, 2
 OBS_DENSITY, OBS_MOMENTUM, OBS_NORM, OBS_G2_MOMENTUM = 0, 1, 2, 3
 
@@ -24,6 +24,7 @@ EXPORTS = [
     "ggp_launch_count", "ggp_host_alloc", "ggp_host_free", "ggp_device_bytes", "ggp_profile_enable",
     "ggp_profile_read", "ggp_debug_l2_flush", "ggp_debug_flush_only",
     "ggp_observe_windowed", "ggp_save_async", "ggp_save_wait", "ggp_checkpoint_bytes", "ggp_checkpoint_save", "ggp_checkpoint_load",
+    "ggp_step_dense", "ggp_host_register", "ggp_host_unregister", "ggp_profile_steps_enable", "ggp_profile_steps_read",
 ]
 
 
@@ -48,6 +49,7 @@ class GgpDesc(C.Structure):
         ("slab_nranks", C.c_int32), ("slab_rank", C.c_int32),
         ("noise_alpha", ((C.c_double * 2) * 2) * 2), ("noise_profile", C.c_void_p),
         ("disp_sep_tol", C.c_double),
+        ("disp_axes", C.c_void_p * 3),
     ]
 
 
@@ -107,6 +109,11 @@ def load():
     lib.ggp_debug_l2_flush.argtypes = [vp, C.c_uint64]
     lib.ggp_debug_flush_only.argtypes = [vp, i64, C.POINTER(C.c_float)]
     lib.ggp_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.ggp_step_dense.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(vp)]
+    lib.ggp_host_register.argtypes = [vp, C.c_uint64]
+    lib.ggp_host_unregister.argtypes = [vp]
+    lib.ggp_profile_steps_enable.argtypes = [vp, C.c_int, C.c_uint64]
+    lib.ggp_profile_steps_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     _lib = lib
     return lib
 

@@ -8,6 +8,14 @@
 #pragma once
 #include "cplx.cuh"
 
+// tuning knobs: default elements per thread (= radix of a full pass) for fp32 / fp64 lines
+#ifndef GGP_E32
+#define GGP_E32 16
+#endif
+#ifndef GGP_E64
+#define GGP_E64 8
+#endif
+
 namespace ggp {
 
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
@@ -28,7 +36,7 @@ __host__ __device__ constexpr int default_E(int N) {
   // threads; fp64: radix 8, radix 16 where a line would otherwise need more than 256 -- never wider than 64 data registers per component
   // (radix-32 fp64 = 128 data registers spills), so the longest fp64 lines take 512 threads instead.
   const bool f32 = sizeof(T) == 4 || IsPacked<T>::value;
-  int e = f32 ? 16 : 8;
+  int e = f32 ? GGP_E32 : GGP_E64;
   const int emax = f32 ? 32 : 16;
   // fp32 lines may take up to 512 threads: radix 32 for N = 8192 needed 151 registers in the row kernel (one
   // 256-thread CTA = 8 warps per SM); radix 16 with 512 threads keeps 64 registers and 32 warps per SM

@@ -297,7 +297,7 @@ struct PlanBase {
   virtual int create(const ggp_desc& d) = 0;
   virtual int set_state(const void* const* u) = 0;
   virtual int get_state(void* const* u) = 0;
-  virtual int step(int64_t nsteps, const double* amp, const void* const* noise) = 0;
+  virtual int step(int64_t nsteps, const double* amp, const void* const* noise, const void* const* profiles = nullptr) = 0;
   virtual int observe(int kind, double* out) = 0;
   virtual int observe_windowed(const double* w1, const double* w2, double* out) = 0;
   virtual void* state_ptr(int c) = 0;
@@ -328,6 +328,50 @@ struct PlanBase {
   // measurement aid: evict L2 after every kernel (timing hygiene for working sets smaller than L2)
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // step-level windows (ggp_profile_steps_*): one event pair per steady-state step, optional flush BETWEEN windows
+  bool step_windows = false;
+  void* sflush_buf = nullptr;
+  size_t sflush_bytes = 0;
+  std::vector<cudaEvent_t> sev;
+  std::vector<int64_t> sev_steps;   // steps covered by each window (1 for 2-D/3-D, the chunk length for 1-D)
+  double steps_ms = 0;
+  int64_t steps_n = 0;
+  bool window_open = false;
+
+  int window_begin(int64_t nsteps_covered = 1) {
+    if (!step_windows || window_open) return 0;
+    cudaEvent_t a;
+    GGP_CUDA(cudaEventCreate(&a));
+    sev.push_back(a);
+    sev_steps.push_back(nsteps_covered);
+    GGP_CUDA(cudaEventRecord(a, stream));
+    window_open = true;
+    return 0;
+  }
+  int window_end() {
+    if (!step_windows || !window_open) return 0;
+    cudaEvent_t b;
+    GGP_CUDA(cudaEventCreate(&b));
+    sev.push_back(b);
+    GGP_CUDA(cudaEventRecord(b, stream));
+    window_open = false;
+    if (sflush_buf) GGP_CUDA(cudaMemsetAsync(sflush_buf, 0, sflush_bytes, stream));
+    return 0;
+  }
+  int windows_collect() {
+    GGP_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i + 1 < sev.size(); i += 2) {
+      float ms = 0;
+      GGP_CUDA(cudaEventElapsedTime(&ms, sev[i], sev[i + 1]));
+      steps_ms += ms;
+      steps_n += sev_steps[i / 2];
+    }
+    for (cudaEvent_t e : sev) cudaEventDestroy(e);
+    sev.clear();
+    sev_steps.clear();
+    window_open = false;
+    return 0;
+  }
 
   int prof_begin(int cls) {
     if (!profiling) return 0;
@@ -385,6 +429,13 @@ struct PlanT : PlanBase {
   int pump_kind = 0, noise_kind = 0, noise_real = 0;
   std::complex<double> amp_prev = 0;
   uint64_t half_ctr = 0;
+  // dense time-dependent pump: ring of three profile buffers (F_{k-1}, F_k, F_{k+1}: the fused contiguous-axis
+  // kernel applies two half-steps), SoA planes of T; pd_k = index of the latest profile (F_0 = primed at init)
+  cpx<T>* pdense[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  int pump_ncomp = 0, table_prec = GGP_C128;
+  uint64_t pd_k = 0;
+  cpx<T>* pd_pin[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // page-locked staging, one per ring slot
+  cudaEvent_t pd_ev[3] = {nullptr, nullptr, nullptr};                                   // H2D copy of that slot done
   HalfStep<T>* hs_dev = nullptr;
   size_t hs_cap = 0;
   void* xi_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
@@ -435,9 +486,16 @@ struct PlanT : PlanBase {
     }
     if (snap_ready) cudaEventDestroy(snap_ready);
     if (copy_done) cudaEventDestroy(copy_done);
+    for (int r = 0; r < 3; ++r) {
+      if (pd_ev[r]) cudaEventDestroy(pd_ev[r]);
+      for (int c = 0; c < 2; ++c)
+        if (pd_pin[r][c]) cudaFreeHost(pd_pin[r][c]);
+    }
     for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     for (void* p : allocs) cudaFree(p);
     if (flush_buf) cudaFree(flush_buf);
+    if (sflush_buf) cudaFree(sflush_buf);
+    for (cudaEvent_t e : sev) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (cudaEvent_t e : pev) cudaEventDestroy(e);
@@ -513,6 +571,13 @@ struct PlanT : PlanBase {
     if (d.disp_sep_tol > 0) tol = d.disp_sep_tol;  // the host verified in Float64 that D is a sum over axes (ggp.h)
     if (const char* e = getenv("GGP_SEP_TOL")) tol = atof(e);
     if (!(emax <= tol * dmax)) return 0;
+    return upload_sep(perp, line);
+  }
+
+  // device copies of the two factors of a separable exp_D; 1/prod(n) (the reference's ScaledPlan, src/misc.jl:56)
+  // is folded into D_perp
+  int upload_sep(const std::vector<std::complex<double>>& perp, const std::vector<std::complex<double>>& line) {
+    const long long np = (long long)perp.size(), nl = (long long)line.size();
     std::vector<cpx<T>> hp((size_t)np), hl((size_t)nl);
     const double sc = 1.0 / ((double)nspatial * P);
     for (long long q = 0; q < np; ++q) hp[(size_t)q] = mk<T>((T)(perp[(size_t)q].real() * sc), (T)(perp[(size_t)q].imag() * sc));
@@ -534,6 +599,42 @@ struct PlanT : PlanBase {
     }
     sep = true;
     return 0;
+  }
+
+  // GGP_TABLE_SEP_AXES: exp_D(k) = prod_a disp_axes[a][k_a] handed over as d short vectors (include/ggp.h)
+  int setup_sep_axes(const ggp_desc& d) {
+    for (int a = 0; a < ndim; ++a)
+      if (!d.disp_axes[a]) return fail(GGP_ERR_INVALID, "disp_axes[a] is NULL (GGP_TABLE_SEP_AXES)");
+    auto get = [&](int a, long long i) -> std::complex<double> {
+      if (d.table_precision == GGP_C128) return ((const std::complex<double>*)d.disp_axes[a])[i];
+      const std::complex<float> z = ((const std::complex<float>*)d.disp_axes[a])[i];
+      return std::complex<double>(z.real(), z.imag());
+    };
+    if (ndim == 1) {
+      std::vector<cpx<T>> h((size_t)n[0]);
+      const double sc = 1.0 / (double)nspatial;
+      for (long long i = 0; i < n[0]; ++i) {
+        const std::complex<double> z = get(0, i) * sc;
+        h[(size_t)i] = mk<T>((T)z.real(), (T)z.imag());
+      }
+      int rc = dalloc((void**)&D[0], sizeof(cpx<T>) * h.size());
+      if (rc) return rc;
+      GGP_CUDA(cudaMemcpy(D[0], h.data(), sizeof(cpx<T>) * h.size(), cudaMemcpyHostToDevice));
+      return 0;
+    }
+    const long long nl = slab ? n3g : n[ndim - 1], np = nspatial / nl;
+    std::vector<std::complex<double>> perp((size_t)np), line((size_t)nl);
+    for (long long l = 0; l < nl; ++l) line[(size_t)l] = get(ndim - 1, l);
+    if (ndim == 2) {
+      for (long long q = 0; q < np; ++q) perp[(size_t)q] = get(0, q);
+    } else {
+      const long long m2 = slab ? n2loc : n[1], off2 = slab ? (long long)prank * n2loc : 0;
+      for (long long j = 0; j < m2; ++j) {
+        const std::complex<double> dj = get(1, off2 + j);
+        for (long long i = 0; i < n[0]; ++i) perp[(size_t)(i + n[0] * j)] = get(0, i) * dj;
+      }
+    }
+    return upload_sep(perp, line);
   }
 
   static int ncols_of(int kind, int M) {
@@ -606,7 +707,10 @@ struct PlanT : PlanBase {
     // tables.  The inverse transform is unnormalised on the device; the reference's 1/prod(n)
     // (ScaledPlan, src/misc.jl:56) is folded into exp_D -- exact for power-of-two sizes.
     int rc;
-    if (dkind != GGP_TABLE_NONE) {
+    if (dkind == GGP_TABLE_SEP_AXES) {
+      if ((rc = setup_sep_axes(d))) return rc;
+      dkind = GGP_TABLE_SCALAR;   // from here on: a scalar table that (for ndim >= 2) exists only as its two factors
+    } else if (dkind != GGP_TABLE_NONE) {
       if (!d.disp_table) return fail(GGP_ERR_INVALID, "disp_table is NULL");
       // (slab: the table arrives in the y-slab layout (n1, n2loc, n3g); same number of points as the z-slab)
       if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / ((double)nspatial * P), D))) return rc;
@@ -691,7 +795,19 @@ struct PlanT : PlanBase {
       for (int i = 0; i < 4; ++i) pw.expV[i] = V[i];
     }
     pump_kind = d.pump_kind;
-    if (pump_kind != GGP_PUMP_NONE) {
+    pump_ncomp = d.pump_ncomp;
+    table_prec = d.table_precision;
+    if (pump_kind == GGP_PUMP_DENSE) {
+      if (!d.pump_table) return fail(GGP_ERR_INVALID, "pump_table is NULL");
+      if (d.pump_ncomp != 1 && d.pump_ncomp != M) return fail(GGP_ERR_INVALID, "pump_ncomp must be 1 or ncomp");
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < pump_ncomp; ++c)
+          if ((rc = dalloc((void**)&pdense[r][c], sizeof(cpx<T>) * (size_t)nspatial))) return rc;
+      pw.pump = pump_ncomp == 1 ? 1 : 2;
+      pw.pump_dense = 1;
+      pd_k = 0;
+      if ((rc = upload_profile(d.pump_table, 0))) return rc;   // F_0 = pump at tspan[1] (src/strang_splitting.jl:58)
+    } else if (pump_kind != GGP_PUMP_NONE) {
       if (!d.pump_table) return fail(GGP_ERR_INVALID, "pump_table is NULL");
       if (d.pump_ncomp != 1 && d.pump_ncomp != M) return fail(GGP_ERR_INVALID, "pump_ncomp must be 1 or ncomp");
       if ((rc = upload_table(d.pump_table, d.table_precision, d.pump_ncomp, 1.0, S))) return rc;
@@ -917,6 +1033,8 @@ struct PlanT : PlanBase {
     return (int64_t)(sizeof(CkptHeader) + (size_t)M * sizeof(cpx<T>) * (size_t)nspatial * (size_t)nbatch);
   }
   int checkpoint_save(void* blob, uint64_t capacity) override {
+    if (pump_kind == GGP_PUMP_DENSE)
+      return fail(GGP_ERR_UNSUPPORTED, "checkpoints of dense-pump plans are not supported (F_now is a full profile, not an amplitude)");
     if ((int64_t)capacity < checkpoint_bytes()) return fail(GGP_ERR_INVALID, "checkpoint buffer too small (ggp_checkpoint_bytes)");
     CkptHeader h;
     memset(&h, 0, sizeof(h));
@@ -959,6 +1077,36 @@ struct PlanT : PlanBase {
     return 0;
   }
 
+  // dense pump: host profile (point-major, then component; table_precision) -> ring slot, SoA planes of T
+  int upload_profile(const void* host, int slot) {
+    if (!host) return fail(GGP_ERR_INVALID, "pump profile pointer is NULL");
+    if (!pd_ev[slot]) {
+      GGP_CUDA(cudaEventCreateWithFlags(&pd_ev[slot], cudaEventDisableTiming));
+      for (int c = 0; c < pump_ncomp; ++c) GGP_CUDA(cudaMallocHost((void**)&pd_pin[slot][c], sizeof(cpx<T>) * (size_t)nspatial));
+    } else {
+      GGP_CUDA(cudaEventSynchronize(pd_ev[slot]));   // the previous transfer out of this staging buffer has finished
+    }
+    for (int c = 0; c < pump_ncomp; ++c) {
+      cpx<T>* pd_stage = pd_pin[slot][c];
+      if (table_prec == GGP_C128) {
+        const std::complex<double>* h = (const std::complex<double>*)host;
+        for (long long i = 0; i < nspatial; ++i) {
+          const std::complex<double> z = h[i * pump_ncomp + c];
+          pd_stage[(size_t)i] = mk<T>((T)z.real(), (T)z.imag());
+        }
+      } else {
+        const std::complex<float>* h = (const std::complex<float>*)host;
+        for (long long i = 0; i < nspatial; ++i) {
+          const std::complex<float> z = h[i * pump_ncomp + c];
+          pd_stage[(size_t)i] = mk<T>((T)z.real(), (T)z.imag());
+        }
+      }
+      GGP_CUDA(cudaMemcpyAsync(pdense[slot][c], pd_stage, sizeof(cpx<T>) * (size_t)nspatial, cudaMemcpyHostToDevice, stream));
+    }
+    GGP_CUDA(cudaEventRecord(pd_ev[slot], stream));
+    return 0;
+  }
+
   // half-step `half` (0/1) of the step whose pump amplitudes are (a_now, a_next)
   HalfStep<T> make_half(std::complex<double> a_now, std::complex<double> a_next, int slot) {
     HalfStep<T> h;
@@ -967,6 +1115,7 @@ struct PlanT : PlanBase {
     h.fnow = mk<T>((T)(q * a_now.real()), (T)(q * a_now.imag()));
     h.fnext = mk<T>((T)(q * a_next.real()), (T)(q * a_next.imag()));
     h.ctr = (uint32_t)half_ctr;
+    h.ctr_hi = (uint32_t)(half_ctr >> 32);
     h.apply = has_pointwise ? 1 : 0;
     h.xi[0] = xi_dev[slot][0];
     h.xi[1] = xi_dev[slot][1];
@@ -1264,9 +1413,12 @@ struct PlanT : PlanBase {
     return 0;
   }
 
-  int step(int64_t nsteps, const double* amp, const void* const* noise) override {
+  int step(int64_t nsteps, const double* amp, const void* const* noise, const void* const* profiles) override {
     if (nsteps <= 0) return 0;
     if (noise && noise_kind == GGP_NOISE_NONE) return fail(GGP_ERR_INVALID, "noise_host given but the plan has no noise term");
+    const bool dense = pump_kind == GGP_PUMP_DENSE;
+    if (dense && !profiles) return fail(GGP_ERR_INVALID, "GGP_PUMP_DENSE plans are stepped with ggp_step_dense (pump profiles per half-step)");
+    if (!dense && profiles) return fail(GGP_ERR_INVALID, "ggp_step_dense on a plan without a dense pump");
     pw.noise = noise_kind == GGP_NOISE_NONE ? NOISE_OFF : (noise ? NOISE_HOST : NOISE_PHILOX);
     auto amps = [&](int64_t s, int half) -> std::complex<double> {
       if (pump_kind == GGP_PUMP_NONE) return 0.0;
@@ -1274,21 +1426,38 @@ struct PlanT : PlanBase {
       return std::complex<double>(amp[2 * (2 * s + half)], amp[2 * (2 * s + half) + 1]);
     };
     int rc;
+    // the next half-step in the reference's order: pump pair (F_now, F_next) = (previous, this one's)  (src/misc.jl:39-42)
+    auto next_half = [&](int64_t s, int half, int slot, HalfStep<T>* out) -> int {
+      if (dense) {
+        const int ring = (int)((pd_k + 1) % 3);
+        int e = upload_profile(profiles[2 * s + half], ring);
+        if (e) return e;
+        ++pd_k;
+        *out = make_half(1.0, 1.0, slot);
+        for (int c = 0; c < pump_ncomp; ++c) {
+          out->pd_now[c] = pdense[(pd_k + 2) % 3][c];   // F_{k-1}
+          out->pd_next[c] = pdense[pd_k % 3][c];        // F_k
+        }
+        return 0;
+      }
+      const std::complex<double> a = amps(s, half);
+      *out = make_half(amp_prev, a, slot);
+      amp_prev = a;
+      return 0;
+    };
     if (ndim == 1) {
-      const int64_t chunk_max = noise ? 1 : 4096;
+      const int64_t chunk_max = (noise || dense) ? 1 : 4096;
       std::vector<HalfStep<T>> hs;
       for (int64_t s0 = 0; s0 < nsteps; s0 += chunk_max) {
         const int64_t cn = std::min<int64_t>(chunk_max, nsteps - s0);
         hs.resize((size_t)(2 * cn));
         for (int64_t s = 0; s < cn; ++s) {
-          const std::complex<double> a1 = amps(s0 + s, 0), a2 = amps(s0 + s, 1);
           if (noise) {
             if ((rc = upload_noise(noise, s0 + s, 0, 0))) return rc;
             if ((rc = upload_noise(noise, s0 + s, 1, 1))) return rc;
           }
-          hs[(size_t)(2 * s)] = make_half(amp_prev, a1, 0);
-          hs[(size_t)(2 * s + 1)] = make_half(a1, a2, 1);
-          amp_prev = a2;
+          if ((rc = next_half(s0 + s, 0, 0, &hs[(size_t)(2 * s)]))) return rc;
+          if ((rc = next_half(s0 + s, 1, 1, &hs[(size_t)(2 * s + 1)]))) return rc;
         }
         if ((rc = ensure_hs((size_t)(2 * chunk_max)))) return rc;
         GGP_CUDA(cudaMemcpyAsync(hs_dev, hs.data(), sizeof(HalfStep<T>) * hs.size(), cudaMemcpyHostToDevice, stream));
@@ -1303,10 +1472,12 @@ struct PlanT : PlanBase {
         p.nsteps = (int)cn;
         for (int i = 0; i < 4; ++i) p.D[i] = D[i];
         p.dkind = dkind;
+        if ((rc = window_begin(cn))) return rc;
         if ((rc = prof_begin(KC_ONED))) return rc;
         GGP_LAUNCH(dispatch_oned<T>((int)n[0], M, pw_variant(), p, stream), "oned_kernel");
         ++launches;
         if ((rc = prof_end())) return rc;
+        if ((rc = window_end())) return rc;
       }
       return 0;
     }
@@ -1315,20 +1486,28 @@ struct PlanT : PlanBase {
     memset(&none, 0, sizeof(none));
     HalfStep<T> prev2 = none;
     for (int64_t s = 0; s < nsteps; ++s) {
-      const std::complex<double> a1 = amps(s, 0), a2 = amps(s, 1);
       if (noise && (rc = upload_noise(noise, s, 0, 0))) return rc;
-      const HalfStep<T> h1 = make_half(amp_prev, a1, 0);
+      HalfStep<T> h1;
+      if ((rc = next_half(s, 0, 0, &h1))) return rc;
       if (dkind == GGP_TABLE_NONE) {
+        // no dispersion: both half-steps of step s in one point-wise launch.  (Philox: the two then draw from the
+        // (z,w) and (x,y) words of ONE call, whereas with a dispersion table a call is shared by the trailing
+        // half-step of step s and the leading one of step s+1 -- distinct draws either way, different streams.)
         if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
-        const HalfStep<T> h2 = make_half(a1, a2, 1);
-        amp_prev = a2;
-        if (has_pointwise && (rc = run_row(false, false, h1, h2))) return rc;
+        HalfStep<T> h2;
+        if ((rc = next_half(s, 1, 1, &h2))) return rc;
+        if (has_pointwise) {
+          if ((rc = window_begin())) return rc;
+          if ((rc = run_row(false, false, h1, h2))) return rc;
+          if ((rc = window_end())) return rc;
+        }
         continue;
       }
       if ((rc = run_row(s > 0, true, prev2, h1))) return rc;
+      if (s > 0 && (rc = window_end())) return rc;     // closes the window of step s-1
       if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
-      prev2 = make_half(a1, a2, 1);
-      amp_prev = a2;
+      if ((rc = next_half(s, 1, 1, &prev2))) return rc;
+      if ((rc = window_begin())) return rc;            // step s: strided pass(es) + the contiguous-axis kernel that closes it
       if (ndim == 2) {
         if ((rc = run_str(1, 1))) return rc;
       } else if (!slab) {
@@ -1349,7 +1528,10 @@ struct PlanT : PlanBase {
         if ((rc = run_str(1, 2))) return rc;
       }
     }
-    if (dkind != GGP_TABLE_NONE && (rc = run_row(true, false, prev2, none))) return rc;
+    if (dkind != GGP_TABLE_NONE) {
+      if ((rc = run_row(true, false, prev2, none))) return rc;
+      if ((rc = window_end())) return rc;
+    }
     return 0;
   }
 
@@ -1514,7 +1696,7 @@ using namespace ggp;
 
 extern "C" {
 
-int ggp_version(void) { return 100; }
+int ggp_version(void) { return 200; }
 
 int ggp_device_count(void) {
   int n = 0;
@@ -1608,6 +1790,11 @@ int ggp_step(ggp_plan* p, int64_t nsteps, const double* amp, const void* const* 
   GGP_ENTER(p);
   return p->impl->step(nsteps, amp, noise);
 }
+int ggp_step_dense(ggp_plan* p, int64_t nsteps, const void* const* profiles, const void* const* noise) {
+  GGP_ENTER(p);
+  if (nsteps > 0 && !profiles) return fail(GGP_ERR_INVALID, "null pump profiles");
+  return p->impl->step(nsteps, nullptr, noise, profiles);
+}
 int ggp_synchronize(ggp_plan* p) {
   GGP_ENTER(p);
   GGP_CUDA(cudaStreamSynchronize(p->impl->stream));
@@ -1692,6 +1879,58 @@ void* ggp_host_alloc(uint64_t bytes) {
 }
 int ggp_host_free(void* q) {
   if (q) GGP_CUDA(cudaFreeHost(q));
+  return 0;
+}
+
+int ggp_host_register(void* q, uint64_t bytes) {
+  if (!q) return fail(GGP_ERR_INVALID, "null pointer");
+  cudaError_t e = cudaHostRegister(q, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GGP_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+int ggp_host_unregister(void* q) {
+  if (!q) return 0;
+  cudaError_t e = cudaHostUnregister(q);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GGP_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int ggp_profile_steps_enable(ggp_plan* p, int on, uint64_t flush_bytes) {
+  GGP_ENTER(p);
+  PlanBase* b = p->impl;
+  GGP_CUDA(cudaStreamSynchronize(b->stream));
+  for (cudaEvent_t e : b->sev) cudaEventDestroy(e);
+  b->sev.clear();
+  b->sev_steps.clear();
+  b->window_open = false;
+  if (b->sflush_buf) {
+    cudaFree(b->sflush_buf);
+    b->sflush_buf = nullptr;
+    b->sflush_bytes = 0;
+  }
+  b->step_windows = on != 0;
+  if (on) {
+    b->steps_ms = 0;
+    b->steps_n = 0;
+    if (flush_bytes) {
+      GGP_CUDA(cudaMalloc(&b->sflush_buf, flush_bytes));
+      b->sflush_bytes = flush_bytes;
+    }
+  }
+  return 0;
+}
+int ggp_profile_steps_read(ggp_plan* p, double* ms_total, int64_t* windows) {
+  GGP_ENTER(p);
+  int rc = p->impl->windows_collect();
+  if (rc) return rc;
+  if (ms_total) *ms_total = p->impl->steps_ms;
+  if (windows) *windows = p->impl->steps_n;
   return 0;
 }
 

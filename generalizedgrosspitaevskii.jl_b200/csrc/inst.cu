@@ -250,7 +250,9 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
     static const int pf_env = getenv("GGP_STR_PF") ? atoi(getenv("GGP_STR_PF")) : 0;
     if (p.tma && !p.scatter && pf_env > 0) p.pf_dist = pf_env;
   }
-  auto k = str_kernel<T, N, M>;
+  // the default geometry runs the instantiation with a compile-time tile width (GGP_STR_WRT=1: always the generic one)
+  static const bool wrt = getenv("GGP_STR_WRT") != nullptr;
+  auto k = (W == K::WDEF && !wrt) ? str_kernel<T, N, M, K::WDEF> : str_kernel<T, N, M, 0>;
   int e = set_smem(k, smem);
   if (e) return e;
   bool use = false;

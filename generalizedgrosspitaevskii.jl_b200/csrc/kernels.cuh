@@ -225,12 +225,15 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], con
     // component serving both half-steps of the pair; then the half-steps as in the deterministic variant.
     uint4 rnd[E][M];
     if (pw.noise == NOISE_PHILOX) {
-      const uint32_t ctr_ref = hs[0].apply ? hs[0].ctr : hs[nh - 1].ctr;
+      const HalfStep<T>& href = hs[0].apply ? hs[0] : hs[nh - 1];
+      // pair index = (64-bit half-step counter + 1) >> 1
+      const unsigned long long pair = ((((unsigned long long)href.ctr_hi << 32) | href.ctr) + 1ull) >> 1;
 #pragma unroll
       for (int m = 0; m < E; ++m)
 #pragma unroll
         for (int c = 0; c < M; ++c)
-          rnd[m][c] = philox_for<T>(gidx0 + m * stride + pw.elem_offset, ctr_ref, c, pw.seed_lo, pw.seed_hi);
+          rnd[m][c] = philox_for<T>(gidx0 + m * stride + pw.elem_offset, (uint32_t)pair, (uint32_t)(pair >> 32), c,
+                                    pw.seed_lo, pw.seed_hi);
     }
 #pragma unroll 1
     for (int h = 0; h < nh; ++h) {
@@ -399,11 +402,15 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
 }
 
 // mode 0: forward only, 1: forward -> x D -> inverse, 2: inverse only
-template <typename T, int N, int M>
+// WT > 0: the tile width is a compile-time constant (the default geometry KCfg::WDEF): shared-memory addresses of
+// the tile pick-up / write-back become one base register + immediate offsets instead of a shift and two adds per
+// element (ncu r01x, 2048^2: 64 of those per thread and direction).  WT = 0: width from the parameters.
+template <typename T, int N, int M, int WT = 0>
 __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::str_bound_blocks(M))
     str_kernel(const __grid_constant__ StrParams<T> p) {
   using K = KCfg<T, N>;
   constexpr int E = K::E, TPL = K::TPL;
+  const int W = WT ? WT : p.W, logW = WT ? ilog2(WT) : p.logW, LS = WT ? K::str_ls_c(WT ? WT : 1) : p.LS;
   constexpr int ROWS = N < 256 ? N : 256;  // rows per TMA box (boxDim <= 256)
   extern __shared__ __align__(128) unsigned char smem_str_raw[];
   unsigned char* const smem_raw = smem_str_raw;
@@ -417,14 +424,14 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
     __syncthreads();
   }
 
-  const int xw = threadIdx.x & (p.W - 1), t = threadIdx.x >> p.logW;
+  const int xw = threadIdx.x & (W - 1), t = threadIdx.x >> logW;
   const long long g = blockIdx.x;
   const long long xt = g % p.ntx, o = g / p.ntx;
   const long long o1 = o % p.no1, o2 = o / p.no1;
-  const long long off = xt * p.W + xw + o1 * p.s1 + o2 * p.s2 + (long long)t * p.ls;
-  const long long toff = xt * p.W + xw + o1 * p.ts1 + (long long)t * p.ls;
+  const long long off = xt * W + xw + o1 * p.s1 + o2 * p.s2 + (long long)t * p.ls;
+  const long long toff = xt * W + xw + o1 * p.ts1 + (long long)t * p.ls;
   const long long mstride = (long long)TPL * p.ls;
-  cpx<T>* sl = smem + (size_t)xw * M * p.LS;
+  cpx<T>* sl = smem + (size_t)xw * M * LS;
 
   // Separable exp_D: the per-column factor is fetched now and D_line is copied into shared memory with
   // cp.async while the field loads and the forward transform run -- both are constant tables, so this happens
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   // shared memory: [exchange lines | twiddle table (TW_SMEM) | D_line (dl_smem) | mbarrier (tma)]
   constexpr bool TW_SMEM = K::str_tw_smem(M);
   using Tw = typename TwT<T>::type;
-  unsigned char* const after_lines = smem_raw + K::str_lines_bytes(M, p.W, p.LS);
+  unsigned char* const after_lines = smem_raw + K::str_lines_bytes(M, W, LS);
   const Tw* twp = p.tw;
   const Tw* twc = p.tw + K::TW_COMPACT_OFF;
   const bool tws = K::TW_STAGED > 0 && (TW_SMEM || p.tw_smem);
@@ -475,12 +482,12 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
     // exchange lines; everybody picks its elements up with conflict-free LDS -- the load/store unit sees 2
     // wavefronts per 32 elements instead of one per 32-byte row piece (8 with W = 4, 16 with W = 2)
     if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, (uint32_t)(M * N * p.W * sizeof(cpx<T>)));
+      mbar_expect_tx(bar, (uint32_t)(M * N * W * sizeof(cpx<T>)));
 #pragma unroll 1
       for (int c = 0; c < M; ++c)
 #pragma unroll 1
         for (int r0 = 0; r0 < N; r0 += ROWS)
-          tma_load_4d(smem + ((size_t)c * N + r0) * p.W, &p.map[c], bar, (int)(2 * xt * p.W), p.ax == 1 ? r0 : (int)o1,
+          tma_load_4d(smem + ((size_t)c * N + r0) * W, &p.map[c], bar, (int)(2 * xt * W), p.ax == 1 ? r0 : (int)o1,
                       p.ax == 1 ? (int)o1 : r0, (int)o2);
     }
     // States larger than the L2: the tile that the CTA taking over this SM slot will want (blockIdx + number of
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
       const long long g2 = g + p.pf_dist;
       if (g2 < (long long)gridDim.x) {
         const long long xt2 = g2 % p.ntx, oo = g2 / p.ntx;
-        const long long base = xt2 * p.W + (oo % p.no1) * p.s1 + (oo / p.no1) * p.s2;
+        const long long base = xt2 * W + (oo % p.no1) * p.s1 + (oo / p.no1) * p.s2;
 #pragma unroll 1
         for (int c = 0; c < M; ++c)
 #pragma unroll 1
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
 #pragma unroll
     for (int c = 0; c < M; ++c)
 #pragma unroll
-      for (int m = 0; m < E; ++m) v[c][m] = smem[(((size_t)c * N + t + m * TPL) << p.logW) + xw];
+      for (int m = 0; m < E; ++m) v[c][m] = smem[(((size_t)c * N + t + m * TPL) << logW) + xw];
   } else {
 #pragma unroll
     for (int c = 0; c < M; ++c)
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   const int it0 = p.mode == 2 ? 1 : 0, it1 = p.mode == 0 ? 0 : 1;
 #pragma unroll 1
   for (int it = it0; it <= it1; ++it) {
-    fft_fwd_all<T, N, M, SyncBlock, K::FACT>(v, t, sl, p.LS, twp, it == 1, twc);
+    fft_fwd_all<T, N, M, SyncBlock, K::FACT>(v, t, sl, LS, twp, it == 1, twc);
     if (it == it0 && p.pdl_pos == 2) pdl_launch_dependents();
     if (it == 0 && p.mode == 1) {
       if (p.dkind == KIND_SEP) {
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   }
   if (p.pdl_pos == 3) pdl_launch_dependents();
   if (p.scatter) {
-    const long long dbase = p.dst_base + xt * p.W + xw + o1 * p.dst_s1 + o2 * p.dst_s2;
+    const long long dbase = p.dst_base + xt * W + xw + o1 * p.dst_s1 + o2 * p.dst_s2;
     const int mask = (1 << p.dst_shift) - 1;
 #pragma unroll
     for (int c = 0; c < M; ++c)
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
 #pragma unroll
     for (int c = 0; c < M; ++c)
 #pragma unroll
-      for (int m = 0; m < E; ++m) smem[(((size_t)c * N + t + m * TPL) << p.logW) + xw] = v[c][m];
+      for (int m = 0; m < E; ++m) smem[(((size_t)c * N + t + m * TPL) << logW) + xw] = v[c][m];
     fence_proxy_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
       for (int c = 0; c < M; ++c)
 #pragma unroll 1
         for (int r0 = 0; r0 < N; r0 += ROWS)
-          tma_store_4d(&p.map[c], smem + ((size_t)c * N + r0) * p.W, (int)(2 * xt * p.W), p.ax == 1 ? r0 : (int)o1,
+          tma_store_4d(&p.map[c], smem + ((size_t)c * N + r0) * W, (int)(2 * xt * W), p.ax == 1 ? r0 : (int)o1,
                        p.ax == 1 ? (int)o1 : r0, (int)o2);
       tma_store_commit_and_wait_read();
     }

@@ -21,7 +21,12 @@ struct HalfStep {
   cpx<T> fnow;    // (dt/2) * a_now   (src/kernels.jl:46)
   cpx<T> fnext;   // (dt/2) * a_next  (src/kernels.jl:45)
   const void* xi[2];  // host-fed noise (test mode), one array per component
-  uint32_t ctr;   // global half-step counter (Philox)
+  // dense time-dependent pump (GGP_PUMP_DENSE): F_now / F_next evaluated on the grid by the host for THIS half-step
+  // (the reference's two pump buffers, src/misc.jl:22-42); fnow = fnext = dt/4
+  const void* pd_now[2];
+  const void* pd_next[2];
+  uint32_t ctr;   // global half-step counter (Philox), low word
+  uint32_t ctr_hi;  // bits 32.. of the pair index (folded into the Philox key)
   int apply;      // 0: skip this half-step
 };
 
@@ -36,6 +41,7 @@ struct PointwiseParams {
   int pump_const;      // the pump profile is the same at every grid point (e.g. examples/truncated_wigner.jl:37-39):
   cpx<T> S_const[2];   // its value rides in the parameters and the table is not read
   int pump_zero[2];    // per-component pump (pump == 2): this component's profile is identically zero, skip its loads
+  int pump_dense;      // profiles come from HalfStep::pd_now / pd_next instead of S
   int nl;      // 0 none, 1 real coefficients, 2 complex coefficients
   T nl_c_re[2], nl_c_im[2];
   T nl_g_re[2][2], nl_g_im[2][2];
@@ -124,10 +130,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 // (c+1)>>1 and uses words (x,y) if (c+1) is even, (z,w) otherwise -- the trailing half-step of step n and
 // the leading half-step of step n+1 (the two the fused kernels apply together) share a call.
 // The counter is the GLOBAL element index, so the stream does not depend on how trajectories are sharded.
+// `pair` = (half-step counter + 1) >> 1 as a 64-bit number: low word in the counter, high word XORed into the key
+// (zero for the first 2^33 half-steps, so earlier streams are unchanged).
 template <typename T>
-__device__ __forceinline__ uint4 philox_for(long long gidx, uint32_t ctr, int comp, uint32_t k0, uint32_t k1) {
-  return philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), (ctr + 1u) >> 1,
-                                  (uint32_t)comp), k0, k1);
+__device__ __forceinline__ uint4 philox_for(long long gidx, uint32_t pair_lo, uint32_t pair_hi, int comp, uint32_t k0,
+                                            uint32_t k1) {
+  return philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), pair_lo, (uint32_t)comp),
+                       k0, k1 ^ pair_hi);
 }
 
 // xi with <|xi|^2> = 1 (complex prototype) or <xi^2> = 1 (real prototype): Box-Muller in fp32 with the
@@ -220,12 +229,18 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
     }
   }
   // w = f + (dt/2) a_now S
-  cpx<T> w[M], sv[M];
+  cpx<T> w[M], sv[M], svn[M];
   if (p.pump) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j]
-                           : ((p.pump == 2 && p.pump_zero[j]) ? mk<T>((T)0, (T)0) : p.S[p.pump == 1 ? 0 : j][sidx]);
+      if (p.pump_dense) {
+        sv[j] = ((const cpx<T>*)h.pd_now[p.pump == 1 ? 0 : j])[sidx];
+        svn[j] = ((const cpx<T>*)h.pd_next[p.pump == 1 ? 0 : j])[sidx];
+      } else {
+        sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j]
+                             : ((p.pump == 2 && p.pump_zero[j]) ? mk<T>((T)0, (T)0) : p.S[p.pump == 1 ? 0 : j][sidx]);
+        svn[j] = sv[j];
+      }
       w[j] = f[j] + cmul(h.fnow, sv[j]);
     }
   } else {
@@ -254,7 +269,7 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
   }
   if (p.pump) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, sv[i]);
+    for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, svn[i]);
   }
   if (pw_is_stoch(PWV) && p.noise) {
 #pragma unroll

@@ -318,6 +318,45 @@ def separable_dispersion_tol(f, grid, param, table, rng=None):
     return 1.25 * dev / dmax + 1e-9 if dmax > 0 else 0.0
 
 
+def dispersion_axis_factors(f, grid, param, dt):
+    """GGP_TABLE_SEP_AXES (include/ggp.h): if the scalar dispersion closure is a sum over axes -- verified in Float64 on
+    random grid points, as in `separable_dispersion_tol` -- return the d per-axis factors of
+    exp_D(k) = cis(-dt D(k)) = prod_a cis(-dt D_a(k_a)),  D_1(k_1) = D(k_1, 0, ...),  D_a(k_a) = D(0, .., k_a, ..) - D(0),
+    each evaluated in Float64 on the axis' own grid values; otherwise None.  Used for grids whose full table would
+    not reasonably fit the host (1024^3 ComplexF64 = 16 GiB)."""
+    d = len(grid)
+    g64 = [np.asarray(g, dtype=np.float64) for g in grid]
+    rng = np.random.default_rng(0x5E9)
+    nprobe = 2048
+    idx = [rng.integers(0, len(g), size=nprobe) for g in g64]
+    zero = [np.full(nprobe, g[0]) for g in g64]
+    pts = [g[i] for g, i in zip(g64, idx)]
+
+    def D(p, n):
+        v = f(tuple(p), param)
+        if isinstance(v, (SVector, SMatrix)):
+            return None
+        return np.asarray(v, dtype=np.complex128) + np.zeros(n)
+
+    full, origin = D(pts, nprobe), D(zero, nprobe)
+    if full is None or origin is None:
+        return None
+    acc = full + (d - 1) * origin
+    for a in range(d):
+        acc = acc - D([pts[b] if b == a else zero[b] for b in range(d)], nprobe)
+    scale = max(1e-300, float(np.abs(full).max()))
+    if float(np.abs(acc).max()) > 1e-12 * scale:
+        return None
+    out = []
+    for a in range(d):
+        n = len(g64[a])
+        line = D([g64[b] if b == a else np.full(n, g64[b][0]) for b in range(d)], n)
+        if a > 0:
+            line = line - D([np.full(n, g64[b][0]) for b in range(d)], n)
+        out.append(np.ascontiguousarray(_cis(-np.float64(dt) * line), dtype=np.complex128))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # closure recognition (registered forms, SURVEY §8a)
 # ------------------------------------------------------------------------------------------------
@@ -377,54 +416,104 @@ def recognise_nonlinearity(f, param, M, rng=None):
 
 
 class PumpModel:
-    """F_i(r, t) = S_i(r) a(t): S table (npoints, ncomp) and an amplitude function a(t)."""
+    """The pump closure on the device: either the registered separable form  F_i(r, t) = S_i(r) a(t)  (S table
+    (npoints, ncomp) + amplitude schedule; `dense` False) or, when the closure does not separate, the reference's own
+    procedure -- the closure evaluated on the whole direct grid at every half-step time (evaluate_pump!,
+    src/misc.jl:34-42) -- handed to the library profile by profile (`dense` True, GGP_PUMP_DENSE).
 
-    def __init__(self, f, prob, tspan, times, grid=None):
+    Recognition never decides from a handful of sampled times (a rectangular pulse between two samples
+    was dropped, a transient second profile was lost): the closure is evaluated at K probe points for EVERY scheduled
+    time, F(r_k, t) = a(t) S(r_k) must hold at all of them, and `zero` needs F = 0 at every scheduled time."""
+
+    NPROBE = 12
+
+    def __init__(self, f, prob, tspan, times, grid=None, force_dense=False):
         grid = grid if grid is not None else direct_grid(prob)
         pts = _mesh(grid)
         shape = tuple(len(g) for g in reversed(grid))
         self.f, self.param, self.M = f, prob.param, len(prob.u0)
+        self.grid, self.shape = grid, shape
+        self._pts = pts
 
-        def on_grid(t):
-            val = f(pts, prob.param, t)
-            if isinstance(val, SMatrix):
-                if val.n != 1:
-                    raise UnsupportedForm("matrix-valued pump")
-                val = SVector(val[0, 0])
-            if isinstance(val, SVector):
-                cols = [np.broadcast_to(np.asarray(v, dtype=complex), shape).reshape(-1) for v in val]
-            else:
-                cols = [np.broadcast_to(np.asarray(val, dtype=complex), shape).reshape(-1)]
-            return np.stack(cols, axis=1)
-
+        sched = [tspan[0]] + [t for t in times]
+        # (1) full-grid evaluations at a few times pick the reference profile and the probe points
         cand = [tspan[0], tspan[-1], 0.5 * (tspan[0] + tspan[-1])]
         if len(times):
-            cand += [times[0], times[len(times) // 3], times[2 * len(times) // 3]]
+            cand += [times[(k * (len(times) - 1)) // 7] for k in range(8)]
         best, tref = None, None
         for t in cand:
-            F = on_grid(t)
+            F = self.on_grid(t)
             if best is None or np.abs(F).max() > np.abs(best).max():
                 best, tref = F, t
         self.ncomp = best.shape[1]
         if self.ncomp not in (1, self.M):
             raise UnsupportedForm("pump must return a Number or an SVector of length M")
-        self.zero = np.abs(best).max() == 0
-        flat = np.abs(best).argmax()
+        npts = best.shape[0]
+        mag = np.abs(best).max(axis=1)
+        order = np.argsort(-mag, kind="stable")
+        probe = [int(order[0])] + [int(order[(k * (npts - 1)) // (self.NPROBE - 1)]) for k in range(1, self.NPROBE)]
+        probe += [int((k * (npts - 1)) // (self.NPROBE - 1)) for k in range(self.NPROBE)]      # + a regular spread
+        self.probe = np.array(sorted(set(probe)))
+        multi = np.unravel_index(self.probe, shape)                                              # (i_d, ..., i_1)
+        self._probe_pts = tuple(np.asarray(g)[i] for g, i in zip(grid, reversed(multi)))
+        # (2) the closure at the probe points for every scheduled time
+        vals = np.stack([self._at_probes(t) for t in sched])                                     # (ntimes, K, ncomp)
+        self.zero = bool(np.abs(vals).max() == 0 and np.abs(best).max() == 0)
+        self.dense = False
+        self.S, self.tref = best.copy(), tref
+        self._sched_amp = None
+        if self.zero:
+            return
+        if np.abs(best).max() == 0:                         # all full-grid candidates vanish, but a probe saw the pump
+            k = int(np.abs(vals).max(axis=(1, 2)).argmax())
+            best, tref = self.on_grid(sched[k]), sched[k]
+            self.S, self.tref = best.copy(), tref
+        flat = int(np.abs(best).argmax())
         self.pidx, self.cidx = np.unravel_index(flat, best.shape)
-        self.S = best.copy()                      # a(tref) == 1 by construction
-        self.tref = tref
-        # coordinates of the probe point
-        multi = np.unravel_index(self.pidx, shape)            # (i_d, ..., i_1)
-        self.rpt = tuple(np.asarray(g[i]).reshape(()) for g, i in zip(grid, reversed(multi)))
-        self._ref = best[self.pidx, self.cidx]
-        # verify separability on the full grid at a few other times
-        if not self.zero:
-            for t in cand[:3] + ([times[len(times) // 2]] if len(times) else []):
-                F = on_grid(t)
-                a = self.amp(t)
-                if np.abs(F - a * self.S).max() > 1e-10 * max(np.abs(F).max(), np.abs(self.S).max()):
-                    raise UnsupportedForm("pump is not separable as S(r) a(t) (dense time-dependent pumps are "
-                                          "not a registered form; the B200 backend has no CPU fallback)")
+        self._ref = best[self.pidx, self.cidx]              # a(tref) == 1 by construction
+        multi1 = np.unravel_index(self.pidx, shape)
+        self.rpt = tuple(np.asarray(g[i]).reshape(()) for g, i in zip(grid, reversed(multi1)))
+        if force_dense or os.environ.get("GGP_PUMP_FORCE_DENSE"):
+            self.dense = True
+            return
+        # (3) separability: F(r_k, t) == a(t) S(r_k) at every probe point and every scheduled time ...
+        amps = np.array([self.amp(t) for t in sched])
+        Sk = self.S[self.probe]                                                                  # (K, ncomp)
+        scale = max(np.abs(vals).max(), np.abs(Sk).max() * np.abs(amps).max(), 1e-300)
+        if np.abs(vals - amps[:, None, None] * Sk[None]).max() > 1e-10 * scale:
+            self.dense = True
+            return
+        # ... and on the full grid at the candidate times
+        for t in cand:
+            F = self.on_grid(t)
+            if np.abs(F - self.amp(t) * self.S).max() > 1e-10 * max(np.abs(F).max(), np.abs(self.S).max()):
+                self.dense = True
+                return
+        self._sched_amp = amps
+
+    def on_grid(self, t):
+        """The closure on the whole direct grid at time t: (npoints, ncomp) complex (grid_map!, src/misc.jl:34-37)."""
+        val = self.f(self._pts, self.param, t)
+        if isinstance(val, SMatrix):
+            if val.n != 1:
+                raise UnsupportedForm("matrix-valued pump")
+            val = SVector(val[0, 0])
+        if isinstance(val, SVector):
+            cols = [np.broadcast_to(np.asarray(v, dtype=complex), self.shape).reshape(-1) for v in val]
+        else:
+            cols = [np.broadcast_to(np.asarray(val, dtype=complex), self.shape).reshape(-1)]
+        return np.stack(cols, axis=1)
+
+    def _at_probes(self, t):
+        val = self.f(self._probe_pts, self.param, t)
+        if isinstance(val, SMatrix):
+            val = SVector(val[0, 0])
+        K = len(self.probe)
+        if isinstance(val, SVector):
+            cols = [np.broadcast_to(np.asarray(v, dtype=complex), (K,)) for v in val]
+        else:
+            cols = [np.broadcast_to(np.asarray(val, dtype=complex), (K,))]
+        return np.stack(cols, axis=1)
 
     def amp(self, t):
         if self.zero:
@@ -600,7 +689,19 @@ class StrangSplittingIterator:
         self._result_shape = [(nsaves + self.save_start,) + tuple(x.shape) for x in u0_local]
         self.result = None                                   # allocated page-locked once the library is up
 
-        dkind, dtab = exp_table(prob.dispersion, rg, prob.param, self.dt, M)            # :53
+        # exp_D: the reference's own table (get_exponential, :53) -- except for grids whose table would not
+        # reasonably fit the host, where a dispersion that is a sum over axes is handed over as d per-axis factors
+        # (GGP_TABLE_SEP_AXES; GGP_SEP_AXES_MIN = smallest number of points that takes this route, default 2^26)
+        daxes = None
+        npts_full = int(np.prod(sizes))
+        if (M == 1 and prob.ndim >= 2 and not _absent(prob.dispersion)
+                and npts_full >= int(os.environ.get("GGP_SEP_AXES_MIN", 1 << 26))):
+            rg_full = reciprocal_grid(prob_g) if slab is not None else rg
+            daxes = dispersion_axis_factors(prob.dispersion, rg_full, prob.param, self.dt)
+        if daxes is not None:
+            dkind, dtab = L.TABLE_SEP_AXES, None
+        else:
+            dkind, dtab = exp_table(prob.dispersion, rg, prob.param, self.dt, M)        # :53
         vkind, vtab = exp_table(prob.potential, dg, prob.param, self.dt / 2, M)         # :54
 
         d = L.GgpDesc()
@@ -627,6 +728,9 @@ class StrangSplittingIterator:
         if dkind == L.TABLE_SCALAR and dtype == np.complex64 and slab is None and not os.environ.get("GGP_NO_SEP_HINT"):
             d.disp_sep_tol = separable_dispersion_tol(prob.dispersion, rg, prob.param, dtab)
         d.disp_table = as_c128(dtab) if dtab is not None else None
+        if daxes is not None:
+            for a_, ax_ in enumerate(daxes):
+                d.disp_axes[a_] = as_c128(ax_)
         d.pot_table = as_c128(vtab) if vtab is not None else None
 
         if not _absent(prob.nonlinearity):
@@ -651,22 +755,42 @@ class StrangSplittingIterator:
                 times[i, 1] = t + self.dt
             pm = PumpModel(prob.pump, prob, (self.ts[0], _jl(tspan[-1])), times.reshape(-1), grid=dg_pump)
             self.pump_model = pm
-            d.pump_kind, d.pump_ncomp = L.PUMP_SEPARABLE, pm.ncomp
-            d.pump_table = as_c128(pm.S)
-            a0 = pm.amp(self.ts[0])                                                     # :58
-            d.pump_amp0[0], d.pump_amp0[1] = a0.real, a0.imag
-            amps = np.array([[pm.amp(times[i, 0]), pm.amp(times[i, 1])] for i in range(nsteps)], dtype=np.complex128)
-            if np.all(amps == a0):
-                self.amps = None            # static pump: the library repeats pump_amp0
+            self.pump_times = times
+            if pm.zero:
+                pass                        # F = 0 at every scheduled time: no pump term at all
+            elif pm.dense:
+                # not S(r) a(t): the reference's own procedure, profile by profile (src/misc.jl:34-42)
+                d.pump_kind, d.pump_ncomp = L.PUMP_DENSE, pm.ncomp
+                d.pump_table = as_c128(pm.on_grid(self.ts[0]))                          # :58
             else:
-                self.amps = np.ascontiguousarray(amps)
+                d.pump_kind, d.pump_ncomp = L.PUMP_SEPARABLE, pm.ncomp
+                d.pump_table = as_c128(pm.S)
+                sched = pm._sched_amp                                                   # a(t0), then a at `times`
+                a0 = complex(sched[0])                                                  # :58
+                d.pump_amp0[0], d.pump_amp0[1] = a0.real, a0.imag
+                amps = np.asarray(sched[1:], dtype=np.complex128).reshape(nsteps, 2)
+                if np.all(amps == a0):
+                    self.amps = None        # static pump: the library repeats pump_amp0
+                else:
+                    self.amps = np.ascontiguousarray(amps)
 
         self.noise_real = False
         if not _absent(prob.position_noise_func):
             if _absent(prob.noise_prototype):
                 raise ValueError("position_noise_func needs a noise_prototype")
             eta, alpha, profile = recognise_noise(prob.position_noise_func, prob)
-            proto = prob.noise_prototype[0]
+            protos = tuple(np.asarray(x) for x in prob.noise_prototype)
+            # The reference indexes xi with the leading ndims(xi) indices only (src/kernels.jl:24,27): a prototype
+            # without the batch dims would share one noise field between all trajectories, and mixed real / complex
+            # prototypes draw differently per component.  The device draws one independent stream per (element,
+            # trajectory, component), so only the shapes every shipped example uses are accepted.
+            if len(protos) != M or any(x.shape != prob.u0[0].shape for x in protos):
+                raise UnsupportedForm("noise_prototype must hold one array per component with the shape of u0 "
+                                      "(prototypes without the batch dims share noise between trajectories in the "
+                                      "reference; not a registered form)")
+            if len({np.iscomplexobj(x) for x in protos}) != 1:
+                raise UnsupportedForm("noise_prototype arrays must be all real or all complex")
+            proto = protos[0]
             self.noise_real = not np.iscomplexobj(proto)
             field = bool(np.any(alpha != 0)) or profile is not None
             if field and slab is not None:
@@ -751,13 +875,28 @@ class StrangSplittingIterator:
             assert seg.shape[0] == nsteps, "stepping past the end of the pump schedule"
             amp_ptr = seg.ctypes.data
         nptr = None
+        bufs = None
         if noise_buffers is not None:
             real_t = np.float32 if self.dtype == np.complex64 else np.float64
             want = real_t if self.noise_real else self.dtype
             bufs = [np.ascontiguousarray(b, dtype=want) for b in noise_buffers]
             assert len(bufs) == 2 * nsteps * self.M, "need 2*nsteps*M noise buffers (step, half-step, component)"
             nptr = _ptr_array(bufs)
-        L.check(self.lib.ggp_step(self.handle, nsteps, amp_ptr, nptr))
+        pm = self.pump_model
+        if pm is not None and pm.dense and not pm.zero:
+            # evaluate_pump! on the host for every half-step of the interval (src/misc.jl:34-42), a few steps at a time
+            done = 0
+            while done < nsteps:
+                k = min(8, nsteps - done)
+                i0 = self._step_index + done
+                assert i0 + k <= self.pump_times.shape[0], "stepping past the end of the pump schedule"
+                profs = [np.ascontiguousarray(pm.on_grid(self.pump_times[i0 + i, h]), dtype=np.complex128)
+                         for i in range(k) for h in (0, 1)]
+                sub = None if bufs is None else _ptr_array(bufs[2 * done * self.M:2 * (done + k) * self.M])
+                L.check(self.lib.ggp_step_dense(self.handle, k, _ptr_array(profs), sub))
+                done += k
+        else:
+            L.check(self.lib.ggp_step(self.handle, nsteps, amp_ptr, nptr))
         self._step_index += nsteps
 
     def fetch(self):

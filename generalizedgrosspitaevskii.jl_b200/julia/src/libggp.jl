@@ -6,9 +6,10 @@
 # mirror (../host.py) implements the same logic line for line and IS exercised by the test-suite.
 using Libdl
 
-const GGP_ABI_VERSION = UInt32(3)
+const GGP_ABI_VERSION = UInt32(4)
 const GGP_C64, GGP_C128 = Int32(0), Int32(1)
-const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL = Int32(0), Int32(1), Int32(2), Int32(3)
+const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL, GGP_TABLE_SEP_AXES = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
+const GGP_PUMP_NONE, GGP_PUMP_SEPARABLE, GGP_PUMP_DENSE = Int32(0), Int32(1), Int32(2)
 
 # Mirror of `struct ggp_desc`; field order and types must match include/ggp.h exactly
 # (tests/test_host_logic.py checks the ctypes twin of this struct against the C header).
@@ -47,6 +48,7 @@ struct GgpDesc
     noise_alpha::NTuple{8,Float64}   # GGP_NOISE_FIELD: alpha_ij [i][j][re/im]
     noise_profile::Ptr{Cvoid}        # GGP_NOISE_FIELD: n[1] ComplexF64 values P(point(k1)) or C_NULL (quirk Q2)
     disp_sep_tol::Float64            # 0 = library default; see include/ggp.h (separable dispersion)
+    disp_axes::NTuple{3,Ptr{Cvoid}}  # GGP_TABLE_SEP_AXES (ABI 4): per-axis factors of a scalar exp_D, else C_NULL
 end
 
 const _lib = Ref{Ptr{Cvoid}}(C_NULL)
@@ -138,6 +140,20 @@ function ggp_step(h::Ptr{Cvoid}, nsteps::Integer, amps::Union{Nothing,AbstractMa
             h, nsteps, Ptr{Float64}(pointer(a)), C_NULL))
     end
 end
+
+# GGP_PUMP_DENSE plans (ABI 4): profiles = 2*nsteps host arrays, the pump evaluated on the direct grid at the
+# reference's half-step times (evaluate_pump!, src/misc.jl:34-42), each npoints*ncomp ComplexF64, point-major
+function ggp_step_dense(h::Ptr{Cvoid}, nsteps::Integer, profiles::Vector{Vector{ComplexF64}}, noise=nothing)
+    ptrs = Ptr{Cvoid}[pointer(x) for x in profiles]
+    nptrs = noise === nothing ? Ptr{Cvoid}[] : Ptr{Cvoid}[pointer(x) for x in noise]
+    pn = noise === nothing ? Ptr{Ptr{Cvoid}}(C_NULL) : pointer(nptrs)
+    GC.@preserve profiles ptrs noise nptrs _check(ccall(_sym(:ggp_step_dense), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}), h, nsteps, ptrs, pn))
+end
+
+# Page-lock caller-owned memory (iter.result) so that ggp_save_async is a true asynchronous DMA (ABI 4)
+ggp_host_register(x::Array) = _check(ccall(_sym(:ggp_host_register), Cint, (Ptr{Cvoid}, UInt64), pointer(x), sizeof(x)))
+ggp_host_unregister(x::Array) = _check(ccall(_sym(:ggp_host_unregister), Cint, (Ptr{Cvoid},), pointer(x)))
 
 # TEST MODE: feed the reference's own noise buffers (step, half-step, component order)
 function ggp_step_with_noise(h::Ptr{Cvoid}, nsteps::Integer, amps, noise::Vector{<:Array})

@@ -33,23 +33,37 @@ function recognise_nonlinearity(f, param, ::Val{M}) where {M}
     scalar, c, g
 end
 
-"F(r,t) = S(r)·a(t): returns (S::Matrix{ComplexF64} (ncomp × npoints), ncomp, amp::Function)"
-function recognise_pump(pump, prob, tspan, times)
+"The pump closure on the whole direct grid at time t, point-major then component (grid_map!, src/misc.jl:34-37)"
+function pump_on_grid(pump, prob, t)
     rs = direct_grid(prob)
-    pts = Iterators.product(rs...)
+    vals = [pump(r, prob.param, t) for r in Iterators.product(rs...)]
+    v1 = first(vals)
+    nc = v1 isa Number ? 1 : length(v1)
+    out = Vector{ComplexF64}(undef, nc * length(vals))
+    for (k, v) in enumerate(vals), c in 1:nc
+        out[(k-1)*nc+c] = v isa Number ? v : v[c]
+    end
+    out
+end
+
+"""
+F(r,t) = S(r)·a(t) or a dense pump (host.py: PumpModel).  Returns `(S (ncomp × npoints), ncomp, amp, dense, zero)`.
+Decisions are taken over EVERY scheduled time, never a handful of samples: the closure is evaluated at K probe points
+for all of `times`; `zero` needs F = 0 at all of them, separability needs F(r_k,t) = a(t)·S(r_k) at all of them (plus a
+few full-grid checks).  `dense = true`: the caller evaluates `pump_on_grid` per half-step (GGP_PUMP_DENSE).
+"""
+function recognise_pump(pump, prob, t0, times)
+    rs = direct_grid(prob)
+    pts = collect(Iterators.product(rs...))
     M = length(prob.u0)
     ongrid(t) = begin
-        vals = [pump(r, prob.param, t) for r in pts]
-        v1 = first(vals)
-        nc = v1 isa Number ? 1 : length(v1)
-        S = Matrix{ComplexF64}(undef, nc, length(vals))
-        for (k, v) in enumerate(vals), c in 1:nc
-            S[c, k] = v isa Number ? v : v[c]
-        end
-        S
+        flat = pump_on_grid(pump, prob, t)
+        nc = length(flat) ÷ length(pts)
+        reshape(flat, nc, length(pts))
     end
-    cand = Any[first(tspan), last(tspan), (first(tspan) + last(tspan)) / 2]
-    isempty(times) || append!(cand, (times[1], times[max(1, end ÷ 3)], times[max(1, 2end ÷ 3)]))
+    sched = Any[t0; times]
+    cand = Any[t0]
+    isempty(times) || append!(cand, [times[1+(k*(length(times)-1))÷7] for k in 0:7])
     S, tref = ongrid(cand[1]), cand[1]
     for t in cand[2:end]
         F = ongrid(t)
@@ -57,21 +71,36 @@ function recognise_pump(pump, prob, tspan, times)
     end
     ncomp = size(S, 1)
     (ncomp == 1 || ncomp == M) || error("pump must return a Number or an SVector of length M")
-    if maximum(abs, S) == 0
-        return S, ncomp, t -> zero(ComplexF64)
+    np = length(pts); K = 12
+    mag = vec(maximum(abs, S; dims=1))
+    order = sortperm(mag; rev=true)
+    probe = unique(vcat([order[1+(k*(np-1))÷(K-1)] for k in 0:K-1], [1 + (k * (np - 1)) ÷ (K - 1) for k in 0:K-1]))
+    at(t) = [(v = pump(pts[k], prob.param, t); ComplexF64(v isa Number ? v : v[c])) for c in 1:ncomp, k in probe]
+    vals = [at(t) for t in sched]
+    if maximum(v -> maximum(abs, v), vals) == 0 && maximum(abs, S) == 0
+        return S, ncomp, t -> zero(ComplexF64), false, true
+    end
+    if maximum(abs, S) == 0                      # every full-grid candidate vanishes, but a probe saw the pump
+        tref = sched[argmax(map(v -> maximum(abs, v), vals))]
+        S = ongrid(tref)
     end
     idx = argmax(abs.(S)); cidx, pidx = Tuple(idx)
-    rpt = collect(pts)[pidx]; ref = S[idx]
+    rpt = pts[pidx]; ref = S[idx]
     amp(t) = begin
         v = pump(rpt, prob.param, t)
         ComplexF64(v isa Number ? v : v[cidx]) / ref
     end
-    for t in cand[1:3]                                # separability check on the full grid
-        F = ongrid(t)
-        maximum(abs, F .- amp(t) .* S) ≤ 1e-10 * max(maximum(abs, F), maximum(abs, S)) ||
-            error("pump is not separable as S(r)·a(t) (no CPU fallback)")
+    A = ComplexF64[amp(t) for t in sched]
+    Sk = S[:, probe]
+    scale = max(maximum(v -> maximum(abs, v), vals), maximum(abs, Sk) * maximum(abs, A), floatmin(Float64))
+    for (i, v) in enumerate(vals)
+        maximum(abs, v .- A[i] .* Sk) ≤ 1e-10 * scale || return S, ncomp, amp, true, false
     end
-    S, ncomp, amp
+    for t in cand                                 # ... and on the full grid at the candidate times
+        F = ongrid(t)
+        maximum(abs, F .- amp(t) .* S) ≤ 1e-10 * max(maximum(abs, F), maximum(abs, S)) || return S, ncomp, amp, true, false
+    end
+    S, ncomp, amp, false, false
 end
 
 """

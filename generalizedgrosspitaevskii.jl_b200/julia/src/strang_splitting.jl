@@ -8,7 +8,7 @@
 
 struct StrangSplitting <: FixedTimeSteppingAlgorithm end
 
-mutable struct StrangSplittingIterator{PROB,T,PROG1,PROG2,R,A} <: FixedTimeSteppingIterator
+mutable struct StrangSplittingIterator{PROB,T,PROG1,PROG2,R,A,TT} <: FixedTimeSteppingIterator
     prob::PROB
     dt::T
     ts::Vector{T}
@@ -18,8 +18,11 @@ mutable struct StrangSplittingIterator{PROB,T,PROG1,PROG2,R,A} <: FixedTimeStepp
     given_progress::PROG2
     result::R
     handle::Ptr{Cvoid}
-    amps::A                 # 2 × nsteps ComplexF64, or nothing (static pump / no pump)
+    amps::A                 # 2 × nsteps ComplexF64, or nothing (static pump / no pump / dense pump)
     step_index::Int
+    dense_pump::Bool        # the pump does not separate as S(r)a(t): profiles are evaluated on the host per half-step
+    pump_times::TT          # the reference's pump evaluation times (quirk Q1), 2 per step; nothing without a pump
+    pinned::Bool            # iter.result is page-locked (ggp_host_register)
 end
 
 _kind(::MultiplicativeIdentity) = GGP_TABLE_NONE
@@ -73,22 +76,39 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
     # pump amplitudes at the reference's times: t is incremented BEFORE step! (SURVEY Q1)
     nsteps = nsaves * steps_per_save
     pump_kind = Int32(0); pump_ncomp = Int32(0); sflat = ComplexF64[]; amp0 = (0.0, 0.0); amps = nothing
+    dense_pump = false; pump_times = nothing
     if !(prob.pump isa AdditiveIdentity)
         t = ts[1]; times = Vector{typeof(t)}(undef, 2nsteps)
         for s in 1:nsteps
             t += dt; times[2s-1] = t + dt / 2; times[2s] = t + dt
         end
-        S, ncomp, amp = recognise_pump(prob.pump, prob, tspan, times)
-        pump_kind = Int32(1); pump_ncomp = Int32(ncomp); sflat = vec(S)               # point-major, then component
-        a0 = amp(ts[1]); amp0 = (real(a0), imag(a0))                                  # primed at tspan[1], :58
-        A = ComplexF64[amp(times[k]) for k in 1:2nsteps]
-        amps = all(==(a0), A) ? nothing : reshape(A, 2, nsteps)
+        S, ncomp, amp, dense, zero_pump = recognise_pump(prob.pump, prob, ts[1], times)
+        pump_times = times
+        if zero_pump
+            # F = 0 at every scheduled time: no pump term
+        elseif dense
+            # not S(r)a(t): the reference's own procedure, profile by profile (evaluate_pump!, src/misc.jl:34-42)
+            dense_pump = true
+            pump_kind = GGP_PUMP_DENSE; pump_ncomp = Int32(ncomp)
+            sflat = pump_on_grid(prob.pump, prob, ts[1])                              # primed at tspan[1], :58
+        else
+            pump_kind = GGP_PUMP_SEPARABLE; pump_ncomp = Int32(ncomp); sflat = vec(S) # point-major, then component
+            a0 = amp(ts[1]); amp0 = (real(a0), imag(a0))                              # primed at tspan[1], :58
+            A = ComplexF64[amp(times[k]) for k in 1:2nsteps]
+            amps = all(==(a0), A) ? nothing : reshape(A, 2, nsteps)
+        end
     end
 
     noise_kind = Int32(0); noise_real = Int32(0); eta = ntuple(_ -> 0.0, 4); seed = UInt64(0)
     alpha = ntuple(_ -> 0.0, 8); nprof = ComplexF64[]
     if !(prob.position_noise_func isa AdditiveIdentity)
         e, al, P = recognise_noise(prob.position_noise_func, prob)
+        # the reference indexes ξ with the leading ndims(ξ) indices only (src/kernels.jl:24,27): a prototype without
+        # the batch dims shares one noise field between trajectories; the device draws per (element, trajectory)
+        (length(prob.noise_prototype) == M && all(x -> size(x) == sz, prob.noise_prototype)) ||
+            error("noise_prototype must hold one array per component with the size of u0 (not a registered form)")
+        allequal(map(x -> eltype(x) <: Real, prob.noise_prototype)) ||
+            error("noise_prototype arrays must be all real or all complex")
         field = any(!iszero, al) || P !== nothing
         noise_kind = Int32(field ? 2 : 1); noise_real = Int32(eltype(first(prob.noise_prototype)) <: Real)
         alpha = ntuple(k -> begin
@@ -105,24 +125,49 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
         CT == ComplexF32 ? GGP_C64 : GGP_C128, GGP_C128, Int32(device), Int32(0), C_NULL, Float64(dt),
         dkind, vkind, _ptr(dflat), _ptr(vflat), nl_kind, nl_scalar, nl_c, nl_g,
         pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed, Int32(0), Int32(0),
-        alpha, _ptr(nprof), sep_tol)
+        alpha, _ptr(nprof), sep_tol, (Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL)))
     handle = GC.@preserve dflat vflat sflat nprof ggp_plan_create(desc)
     ggp_set_state(handle, host_u0)                                                    # u = copy.(prob.u0), :48
 
+    # page-lock `result` so that the streaming saves of solve! are asynchronous DMA transfers
+    pinned = false
+    try
+        foreach(ggp_host_register, result); pinned = true
+    catch
+        pinned = false                     # pageable memory still works: the copies then synchronise
+    end
     iter = StrangSplittingIterator(prob, dt, ts, steps_per_save, save_start, _progress, progress, result,
-        handle, amps, 0)
-    finalizer(it -> (it.handle == C_NULL || ggp_plan_destroy(it.handle); it.handle = C_NULL), iter)
+        handle, amps, 0, dense_pump, pump_times, pinned)
+    finalizer(iter) do it
+        it.handle == C_NULL || ggp_plan_destroy(it.handle)
+        it.handle = C_NULL
+    end
     iter
+end
+
+# nsteps steps from the current position of the schedule: amplitudes (separable pump), profiles (dense pump) or nothing
+function _advance!(iter::StrangSplittingIterator, nsteps::Int)
+    i0 = iter.step_index
+    if iter.dense_pump
+        done = 0
+        while done < nsteps                                   # a few steps at a time: 2k full-grid profiles on the host
+            k = min(8, nsteps - done)
+            profs = Vector{ComplexF64}[pump_on_grid(iter.prob.pump, iter.prob, iter.pump_times[2(i0+done+i)-1+h])
+                                       for i in 1:k for h in 0:1]
+            ggp_step_dense(iter.handle, k, profs)
+            done += k
+        end
+    else
+        a = iter.amps === nothing ? nothing : view(iter.amps, :, i0+1:i0+nsteps)
+        ggp_step(iter.handle, nsteps, a)
+    end
+    iter.step_index += nsteps
+    nothing
 end
 
 # step!(iter, t, dt): one Strang step on the device (reference :86-90).  t/dt are accepted for
 # signature compatibility; the pump schedule was fixed at init.
-function step!(iter::StrangSplittingIterator, t, dt)
-    a = iter.amps === nothing ? nothing : view(iter.amps, :, iter.step_index+1:iter.step_index+1)
-    ggp_step(iter.handle, 1, a)
-    iter.step_index += 1
-    nothing
-end
+step!(iter::StrangSplittingIterator, t, dt) = _advance!(iter, 1)
 
 # solve!: the reference's loop (src/fixed_time_stepping.jl:26-54) with the inner `for _ in 1:steps_per_save`
 # batched into one ggp_step call and `map(copy!, slice, iter.u)` replaced by one streaming save per interval
@@ -132,9 +177,7 @@ function solve!(iter::StrangSplittingIterator)
     nd = ndims(first(iter.result))
     t = ts[1]
     for n ∈ 1:size(first(iter.result), nd)-save_start
-        a = iter.amps === nothing ? nothing : view(iter.amps, :, iter.step_index+1:iter.step_index+sps)
-        ggp_step(iter.handle, sps, a)
-        iter.step_index += sps
+        _advance!(iter, sps)
         for _ ∈ 1:sps
             t += dt                                   # accumulated in T exactly like the reference (:44)
             _next!(p)
@@ -144,6 +187,9 @@ function solve!(iter::StrangSplittingIterator)
         ts[n+1] = t
     end
     ggp_save_wait(iter.handle)
+    if iter.pinned
+        foreach(ggp_host_unregister, iter.result); iter.pinned = false
+    end
     _finish!(p, iter.given_progress)
     ts[begin+1-save_start:end], iter.result
 end

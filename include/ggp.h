@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGP_ABI_VERSION 3u
+#define GGP_ABI_VERSION 4u
 
 typedef enum ggp_status {
   GGP_OK = 0,
@@ -59,7 +59,9 @@ typedef enum ggp_table_kind {
   GGP_TABLE_NONE = 0,   /* AdditiveIdentity -> multiplicativeIdentity (src/misc.jl:12) */
   GGP_TABLE_SCALAR = 1, /* Number: one complex per point */
   GGP_TABLE_DIAG = 2,   /* SVector{M}: M complex per point (elementwise product, src/kernels.jl:10) */
-  GGP_TABLE_FULL = 3    /* SMatrix{M,M}: M*M complex per point, column-major (m11,m21,m12,m22) */
+  GGP_TABLE_FULL = 3,   /* SMatrix{M,M}: M*M complex per point, column-major (m11,m21,m12,m22) */
+  GGP_TABLE_SEP_AXES = 4 /* disp_kind only (ABI 4): a scalar exp_D given as one factor per axis,
+                            exp_D(k) = prod_a disp_axes[a][k_a] -- see disp_axes below */
 } ggp_table_kind;
 
 typedef enum ggp_nl_kind {
@@ -69,7 +71,11 @@ typedef enum ggp_nl_kind {
 
 typedef enum ggp_pump_kind {
   GGP_PUMP_NONE = 0,
-  GGP_PUMP_SEPARABLE = 1 /* F_i(r,t) = S_i(r) a(t); a static pump is a(t) = const */
+  GGP_PUMP_SEPARABLE = 1, /* F_i(r,t) = S_i(r) a(t); a static pump is a(t) = const */
+  GGP_PUMP_DENSE = 2      /* any F(r,t): the caller evaluates the pump closure on the direct grid at every half-step
+                             time, exactly as evaluate_pump! does (src/misc.jl:34-42, called from
+                             src/strang_splitting.jl:81), and hands the profiles to ggp_step_dense (ABI 4).
+                             pump_table = the profile at tspan[1] (primed at init, src/strang_splitting.jl:58). */
 } ggp_pump_kind;
 
 typedef enum ggp_noise_kind {
@@ -158,6 +164,12 @@ typedef struct ggp_desc {
      Float64 that the dispersion is a sum over axes passes the measured deviation here so that the fast path is
      kept; 0 = library default. */
   double disp_sep_tol;
+
+  /* GGP_TABLE_SEP_AXES (ABI 4): per-axis factors of a scalar exp_D, disp_axes[a] = n[a] complex numbers of
+     table_precision with exp_D(k) = prod_a disp_axes[a][k_a]; disp_table is ignored.  For dispersions that are a sum
+     over axes (|k|^2/2 + const ...) this replaces the full-grid table -- 16 GiB of host memory for a 1024^3
+     ComplexF64 table -- by d short vectors.  Slab plans pass the GLOBAL axes; the library slices. */
+  const void *disp_axes[3];
 } ggp_desc;
 
 typedef struct ggp_plan ggp_plan;
@@ -184,6 +196,16 @@ int ggp_get_state(ggp_plan *plan, void *const *u_host);
  *               reference's draw order: step, half-step, component (src/misc.jl:44-51).
  */
 int ggp_step(ggp_plan *plan, int64_t nsteps, const double *pump_amp, const void *const *noise_host);
+
+/*
+ * GGP_PUMP_DENSE plans: as ggp_step, but instead of amplitudes the caller passes the pump evaluated on the direct
+ * grid: pump_profiles = 2*nsteps pointers, for step s the profiles at t_s + dt/2 and t_s + dt (the reference's
+ * one-dt-late times), each nspatial * pump_ncomp complex numbers of table_precision laid out like
+ * pump_table (point-major, then component).  The library keeps F_now across calls (src/misc.jl:39-42: the
+ * double-buffer shuffle of evaluate_pump!).  Replaces evaluate_pump! + the pump buffers of the reference for pumps
+ * that do not separate as S(r) a(t).
+ */
+int ggp_step_dense(ggp_plan *plan, int64_t nsteps, const void *const *pump_profiles, const void *const *noise_host);
 
 int ggp_synchronize(ggp_plan *plan);
 
@@ -246,6 +268,10 @@ int ggp_timer_end(ggp_plan *plan, float *milliseconds);
 int64_t ggp_launch_count(ggp_plan *plan);
 void *ggp_host_alloc(uint64_t bytes);
 int ggp_host_free(void *p);
+/* Page-lock / unlock memory the CALLER owns (e.g. the Julia `result` arrays allocated by init,
+   src/strang_splitting.jl:41-43), so that ggp_save_async into it is a true asynchronous DMA (ABI 4). */
+int ggp_host_register(void *p, uint64_t bytes);
+int ggp_host_unregister(void *p);
 /* bytes of device memory the plan owns */
 int64_t ggp_device_bytes(ggp_plan *plan);
 /* Per-kernel-class device timing inside ggp_step (CUDA events around every launch on the plan's
@@ -260,6 +286,14 @@ int ggp_debug_l2_flush(ggp_plan *plan, uint64_t bytes);
 /* Time `count` of those flushes alone (same stream, one event pair): subtracted from a bracketed flushed run. */
 int ggp_debug_flush_only(ggp_plan *plan, int64_t count, float *milliseconds);
 int ggp_profile_read(ggp_plan *plan, double *ms_total, int64_t *launches);
+/* Step-level timing (bench.py's headline): one CUDA-event pair around the kernels of every steady-state step --
+   the strided pass(es) of step s and the contiguous-axis kernel that closes it (inverse FFT_x, trailing V/2 of step s,
+   leading V/2 of step s+1, forward FFT_x) -- so programmatic-launch overlap INSIDE a step is part of the number, and,
+   when flush_bytes > 0, that many bytes are overwritten BETWEEN the windows (outside every event pair) so that each
+   step starts with a cold L2.  The leading kernel of a ggp_step call (V/2 + forward FFT_x only) is outside the
+   windows.  ggp_profile_steps_read: total milliseconds over the windows and their number since enable. */
+int ggp_profile_steps_enable(ggp_plan *plan, int on, uint64_t flush_bytes);
+int ggp_profile_steps_read(ggp_plan *plan, double *ms_total, int64_t *windows);
 
 #ifdef __cplusplus
 }

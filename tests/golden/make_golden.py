@@ -63,7 +63,29 @@ def run_oracle(name, record=None):
     return ts, sol
 
 
+def export_inputs():
+    """Inputs for tests/golden/make_golden_ref.jl (the REAL reference, run by whoever has Julia): every case's
+    initial fields and, for the stochastic cases, the noise arrays in the reference's draw order, as plain .npy."""
+    import ggp_oracle as O
+    dst = os.path.join(HERE, "ref_inputs_v1")
+    os.makedirs(dst, exist_ok=True)
+    for name in CASES:
+        pb, seed = build(O, name)
+        for c, x in enumerate(pb["u0"]):
+            np.save(os.path.join(dst, f"{name}__u0_{c}.npy"), np.ascontiguousarray(x))
+        if seed is not None:
+            rec = []
+            run_oracle(name, record=rec)
+            for k, z in enumerate(rec):
+                np.save(os.path.join(dst, f"{name}__xi_{k}.npy"), np.ascontiguousarray(z))
+        print("exported", name)
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
+    if "--export-inputs" in sys.argv:
+        export_inputs()
+        sys.exit(0)
     out = {}
     for name in CASES:
         ts, sol = run_oracle(name)

@@ -134,10 +134,22 @@ def test_closure_recognition(G):
     for t in (0.0, 3.0, 17.5):
         F = np.broadcast_to(np.asarray(prob.pump(pts, prob.param, t), dtype=complex), (256,))
         assert np.allclose(pm.amp(t) * pm.S[:, 0], F, rtol=1e-13, atol=1e-16)
-    bad = lambda x, p, t: np.exp(-(x[0] - t) ** 2)           # travelling pump: not separable
+    assert not pm.dense and not pm.zero
+    bad = lambda x, p, t: np.exp(-(x[0] - t) ** 2)           # travelling pump: not separable -> dense profiles
     prob_bad = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], dispersion=prob.dispersion, pump=bad)
-    with pytest.raises(G.UnsupportedForm):
-        host.PumpModel(bad, prob_bad, (0.0, 10.0), times)
+    pmb = host.PumpModel(bad, prob_bad, (0.0, 10.0), times)
+    assert pmb.dense and not pmb.zero
+    assert np.allclose(pmb.on_grid(3.0)[:, 0], np.exp(-(np.asarray(G.direct_grid(prob_bad)[0]) - 3.0) ** 2))
+    # decisions are taken over EVERY scheduled time, not a handful of samples
+    sched = np.linspace(0.0, 1.0, 201)[1:]
+    pulse = lambda x, p, t: np.exp(-(x[0] - 128.0) ** 2 / 50.0) * (1.0 if 0.41 < t < 0.49 else 0.0)
+    pmp = host.PumpModel(pulse, prob_bad, (0.0, 1.0), sched)
+    assert not pmp.zero and not pmp.dense                     # a rectangular pulse between the old sample times
+    assert pmp.amp(0.45) != 0 and pmp.amp(0.3) == 0
+    trans = lambda x, p, t: np.exp(-(x[0] - 100.0) ** 2 / 50.0) + (0.5 * np.exp(-(x[0] - 160.0) ** 2 / 20.0) if 0.41 < t < 0.49 else 0.0)
+    assert host.PumpModel(trans, prob_bad, (0.0, 1.0), sched).dense     # static profile + transient second profile
+    never = lambda x, p, t: 0.0 * x[0]
+    assert host.PumpModel(never, prob_bad, (0.0, 1.0), sched).zero
     # noise: eta_i(u, r) = P(r) (e_i + sum_j a_ij |u_j|)  (docs/src/stochastic_simulations.md:62-86)
     pbw = P.windowed_ft(G, ntraj=4)
     probw = G.GrossPitaevskiiProblem(pbw["u0"], pbw["lengths"], **pbw["kwargs"])
@@ -203,3 +215,41 @@ def test_separable_dispersion_hint(G):
     vec = lambda ks, p: G.SVector((ks[0] ** 2 + ks[1] ** 2) / 2)
     assert host.separable_dispersion_tol(vec, rg, prob.param, tab) == 0.0
     assert host.separable_dispersion_tol(prob.dispersion, rg[:1], prob.param, tab[:N]) == 0.0   # 1-D: nothing to factor
+
+
+def test_dispersion_axis_factors(G):
+    """GGP_TABLE_SEP_AXES: the per-axis factors multiply to the reference's table (Float64: to rounding) for a
+    dispersion that is a sum over axes -- lossy and offset terms included -- and are refused for anything else."""
+    import importlib
+    host = importlib.import_module("ggp_b200.host")
+    u0 = (np.zeros((8, 16, 32), dtype=np.complex128),)
+    prob = G.GrossPitaevskiiProblem(u0, (5.0, 7.0, 9.0))
+    rg = G.reciprocal_grid(prob)
+    disp = lambda ks, p: (ks[0] ** 2 + 2 * ks[1] ** 2 + ks[2] ** 2) / 2 - 0.3 - 0.05j
+    ax = host.dispersion_axis_factors(disp, rg, None, 0.01)
+    assert ax is not None and [len(a) for a in ax] == [32, 16, 8]
+    kind, tab = host.exp_table(disp, rg, None, np.float64(0.01), 1)
+    prod = ax[2][:, None, None] * ax[1][None, :, None] * ax[0][None, None, :]
+    assert np.abs(prod.reshape(-1) - tab[:, 0]).max() < 1e-14
+    assert host.dispersion_axis_factors(lambda ks, p: ks[0] * ks[1] + ks[2] ** 2, rg, None, 0.01) is None
+    assert host.dispersion_axis_factors(lambda ks, p: G.SVector(ks[0] ** 2 + ks[1] ** 2 + ks[2] ** 2), rg, None, 0.01) is None
+
+
+def test_noise_prototype_shapes_are_checked(G):
+    """prototypes that would share noise between trajectories in the reference (no batch dims), a wrong
+    count or mixed real / complex prototypes are rejected before the plan is created."""
+    import importlib
+    host = importlib.import_module("ggp_b200.host")
+    u0 = (np.zeros((4, 16), dtype=np.complex128),)
+    eta = lambda u, r, p: 0.5
+    for proto in ((np.zeros(16, dtype=np.complex128),),                                           # no batch dim
+                  (np.zeros((4, 16), dtype=np.complex128), np.zeros((4, 16), dtype=np.complex128))):  # wrong count
+        prob = G.GrossPitaevskiiProblem(u0, (10.0,), dispersion=lambda ks, p: ks[0] ** 2, position_noise_func=eta,
+                                        noise_prototype=proto)
+        with pytest.raises(G.UnsupportedForm):
+            G.init(prob, G.StrangSplitting(), (0.0, 0.1), dt=0.05, nsaves=1)
+    u2 = (np.zeros((4, 16), dtype=np.complex128),) * 2
+    prob = G.GrossPitaevskiiProblem(u2, (10.0,), dispersion=lambda ks, p: ks[0] ** 2, position_noise_func=eta,
+                                    noise_prototype=(np.zeros((4, 16)), np.zeros((4, 16), dtype=np.complex128)))
+    with pytest.raises(G.UnsupportedForm):
+        G.init(prob, G.StrangSplitting(), (0.0, 0.1), dt=0.05, nsaves=1)
