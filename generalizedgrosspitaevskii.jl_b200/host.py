@@ -639,7 +639,7 @@ class _PinnedBlock:
 
 class StrangSplittingIterator:
     def __init__(self, prob, tspan, *, dt, nsaves, save_start=True, rng=None, device=-1,
-                 batch_offset=0, stream=None, slab=None, slab_local=False):
+                 batch_offset=0, stream=None, slab=None, slab_local=False, result_buffers=True):
         """slab=(rank, world): 3-D slab decomposition, one process per GPU.  `prob.u0` is the GLOBAL field
         (each rank keeps z-planes [rank*n3/world, (rank+1)*n3/world)), or already this rank's z-slab if
         slab_local=True.  Results / fetch() are the local z-slab.  Attach a communicator
@@ -820,11 +820,12 @@ class StrangSplittingIterator:
         # streaming saves (ggp_save_async) overlap the next save interval.  Julia's trailing save index is the
         # leading NumPy axis over the same memory.
         res = []
-        for x, shp in zip(u0_local, self._result_shape):
-            r = self._pinned_empty(shp, x.dtype)
-            r[...] = x
-            res.append(r)
-        self.result = tuple(res)
+        if result_buffers:                  # (benchmarks of multi-GiB states step without a result array)
+            for x, shp in zip(u0_local, self._result_shape):
+                r = self._pinned_empty(shp, x.dtype)
+                r[...] = x
+                res.append(r)
+        self.result = tuple(res) if result_buffers else None
         self.u = [self._pinned_like(x) for x in u0_local]                               # :48 (pinned staging)
         for dst, src in zip(self.u, u0_local):
             np.copyto(dst, src)

@@ -249,11 +249,21 @@ def kerr3d_slab(ns, N=512, rank=0, world=1, dtype=np.complex64, L=32.0, g=1.0, d
     Y, X = np.meshgrid(rs, rs, indexing="ij")
     gxy = np.exp(-((X - Lr / 2) ** 2 + (Y - Lr / 2) ** 2) / 16).astype(real)
     u0 = np.empty((nz, N, N), dtype=dtype)
-    for k in range(nz):
+
+    def plane(k):
         rng = np.random.default_rng([seed, z0 + k])
         xi = rng.standard_normal((N, N, 2), dtype=np.float32)
         gz = real(np.exp(-((rs[z0 + k] - Lr / 2) ** 2) / 16))
         u0[k] = (gxy * gz) * (1 + real(0.01 / np.sqrt(2)) * (xi[..., 0] + 1j * xi[..., 1]))
+
+    if nz * N * N >= 1 << 24:       # large slabs: planes are independent (one generator each), NumPy releases the GIL
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max(1, min(16, len(os.sched_getaffinity(0))))) as ex:
+            list(ex.map(plane, range(nz)))
+    else:
+        for k in range(nz):
+            plane(k)
 
     def dispersion(ks, param):
         return _sumsq(ks) / 2
