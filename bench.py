@@ -462,9 +462,6 @@ def sharded_block(G, a, world, rank, local, peak, windows):
 
 def main():
     global _DIST, _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -490,6 +487,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)       # (after the re-launch above: the torchrun children must inherit the real stdout)
+    os.dup2(2, 1)
 
     if a.impl == "reference":
         if rank != 0:

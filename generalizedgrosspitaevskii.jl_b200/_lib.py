@@ -50,6 +50,7 @@ class GgpDesc(C.Structure):
         ("noise_alpha", ((C.c_double * 2) * 2) * 2), ("noise_profile", C.c_void_p),
         ("disp_sep_tol", C.c_double),
         ("disp_axes", C.c_void_p * 3),
+        ("mixed_precision_tables", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

@@ -146,6 +146,20 @@ template <typename T>
 __device__ __forceinline__ T cabs2(cpx<T> a) {
   return fma_(a.y, a.y, a.x * a.x);
 }
+// Table loads written as volatile asm: the front end keeps them where they are written, ahead of the arithmetic that
+// consumes them, so a batch of exp_D entries is requested together instead of one element at a time (parked strided
+// kernel, kernels.cuh).
+__device__ __forceinline__ cpx<double> ldg_nc_ordered(const cpx<double>* q) {
+  cpx<double> r;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(q));
+  return r;
+}
+__device__ __forceinline__ cpx<float> ldg_nc_ordered(const cpx<float>* q) {
+  cpx<float> r;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(q));
+  return r;
+}
+
 // Inter-pass twiddle factors and the factors of a separable exp_D.  Default: a plain complex number of the
 // plan's precision.  -DGGP_SPLIT_TWIDDLES (make SPLIT_TW=1): fp32 plans keep the double-precision value as
 // hi + lo (one 16-byte entry, one LDG.128) and multiply with four extra FMAs.  Measured (tools/

@@ -45,9 +45,11 @@ __host__ __device__ constexpr int default_E(int N) {
   return e < N ? e : N;
 }
 
-template <typename T, int N>
+// EO > 0 overrides the default elements-per-thread / radix for one kernel (e.g. the stochastic fp64 row kernel, which is
+// bound by the latency of its Philox / sincos chains and wants twice the warps: KCfg::row_E in kernels.cuh)
+template <typename T, int N, int EO = 0>
 struct LineCfg {
-  static constexpr int E = default_E<T>(N);
+  static constexpr int E = EO > 0 ? (EO < N ? EO : N) : default_E<T>(N);
   static constexpr int TPL = N / E;         // threads per line
   static constexpr int LOGE = ilog2(E);
   // padded length of one line in shared memory: one pad element per E elements keeps the
@@ -66,12 +68,12 @@ struct SyncWarp {
 // Twiddle table layout (built on the host, ggp_api.cu): for every pass after the first, in order,
 // a block of (R-1)*NS entries  tw[off + (r-1)*NS + k] = exp(-2 pi i r k / (NS*R)),  k < NS, 1 <= r < R,
 // so that consecutive lanes (consecutive k) read consecutive addresses.
-template <typename T, int N>
+template <typename T, int N, int EO = 0>
 __host__ __device__ constexpr int twiddle_count(int NS = 1) {
-  constexpr int E = default_E<T>(N);
+  constexpr int E = LineCfg<T, N, EO>::E;
   if (NS >= N) return 0;
   const int R = (N / NS >= E) ? E : N / NS;
-  return (NS > 1 ? (R - 1) * NS : 0) + twiddle_count<T, N>(NS * R);
+  return (NS > 1 ? (R - 1) * NS : 0) + twiddle_count<T, N, EO>(NS * R);
 }
 
 // Long lines (N >= 4096): the late passes (NS >= 256) need (R-1)*NS twiddles -- a table as large as the line
@@ -101,9 +103,9 @@ __host__ __device__ constexpr int twiddle_small_count(int NS = 1) {
 
 // Stockham pass (NS = product of the radices of the earlier passes) and all later passes.
 // DIR = -1 forward (e^{-i k x}), +1 inverse (unnormalised); TWOFF = offset of this pass' twiddles.
-template <typename T, int N, int DIR, typename SYNC, int NS, int TWOFF = 0, bool FACT = false>
+template <typename T, int N, int DIR, typename SYNC, int NS, int TWOFF = 0, bool FACT = false, int EO = 0>
 struct Passes {
-  using Cfg = LineCfg<T, N>;
+  using Cfg = LineCfg<T, N, EO>;
   static constexpr int E = Cfg::E;
   static constexpr int TPL = Cfg::TPL;
   static constexpr int R = (N / NS >= E) ? E : N / NS;
@@ -171,19 +173,19 @@ struct Passes {
     }
     if constexpr (!LASTP) {
       SYNC::sync();
-      Passes<T, N, DIR, SYNC, NS * R, TWOFF + (NS > 1 ? (R - 1) * NS : 0), FACT>::run(v, t, line, tw, twc);
+      Passes<T, N, DIR, SYNC, NS * R, TWOFF + (NS > 1 ? (R - 1) * NS : 0), FACT, EO>::run(v, t, line, tw, twc);
     }
   }
 };
 
 // Transform one line held in registers.  PRESYNC: the shared line may still be read by a previous
 // transform of the same thread group, so synchronise before the first scatter.
-template <typename T, int N, int DIR, typename SYNC, bool PRESYNC, bool FACT = false>
-__device__ __forceinline__ void fft_line(cpx<T> (&v)[LineCfg<T, N>::E], const int t, cpx<T>* __restrict__ line,
+template <typename T, int N, int DIR, typename SYNC, bool PRESYNC, bool FACT = false, int EO = 0>
+__device__ __forceinline__ void fft_line(cpx<T> (&v)[LineCfg<T, N, EO>::E], const int t, cpx<T>* __restrict__ line,
                                          const typename TwT<T>::type* __restrict__ tw,
                                          const typename TwT<T>::type* __restrict__ twc = nullptr) {
-  if (PRESYNC && LineCfg<T, N>::E < N) SYNC::sync();
-  Passes<T, N, DIR, SYNC, 1, 0, FACT>::run(v, t, line, tw, twc);
+  if (PRESYNC && LineCfg<T, N, EO>::E < N) SYNC::sync();
+  Passes<T, N, DIR, SYNC, 1, 0, FACT, EO>::run(v, t, line, tw, twc);
 }
 
 }  // namespace ggp

@@ -413,9 +413,12 @@ struct PlanT : PlanBase {
   double dt = 0;
   cpx<T>* u[2] = {nullptr, nullptr};
   cpx<T>* D[4] = {nullptr, nullptr, nullptr, nullptr};
+  cpx<T>* Daos = nullptr;    // two-component diagonal / matrix exp_D, point-major (StrParams::Daos)
+  int dcols = 0;
   cpx<T>* V[4] = {nullptr, nullptr, nullptr, nullptr};
   cpx<T>* S[2] = {nullptr, nullptr};
   typename TwT<T>::type* tw[3] = {nullptr, nullptr, nullptr};
+  typename TwT<T>::type* tw_row = nullptr;   // twiddles of the row kernel where its radix differs from the default (row_E)
   void* tw2[3] = {nullptr, nullptr, nullptr};  // duplicated twiddles of the packed two-line kernels (fp32 plans)
   bool packed_ok = false;
   int dkind = 0;
@@ -424,6 +427,8 @@ struct PlanT : PlanBase {
   cpx<T>* Dperp = nullptr;
   cpx<T>* Dline = nullptr;
   typename TwT<T>::type* Dsp[2] = {nullptr, nullptr};  // the same factors as hi + lo pairs (fp32 plans)
+  double2* Dq[2] = {nullptr, nullptr};                  // ... and in Float64 (quirk Q6, mixed_precision_tables)
+  bool q6 = false;
   PointwiseParams<T> pw;
   bool has_pointwise = false;
   int pump_kind = 0, noise_kind = 0, noise_real = 0;
@@ -464,6 +469,10 @@ struct PlanT : PlanBase {
   int* bar_err = nullptr;
   unsigned epoch = 0;
   std::vector<void*> ipc_opened;
+  cudaStream_t aux_stream = nullptr;      // second stream of the chunked local phase (slab_iry)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int slab_chunks = 4;
+  bool slab_yocc1 = false;   // GGP_SLAB_YOCC1=1: the chunked scatter pass runs at one CTA per SM (room for the other stream)
   // TMA path of the strided kernel, per strided axis (1, 2)
   bool tma_ok[3] = {false, false, false};
   bool tma_d[3] = {false, false, false};  // exp_D staged by TMA as well
@@ -486,6 +495,12 @@ struct PlanT : PlanBase {
     }
     if (snap_ready) cudaEventDestroy(snap_ready);
     if (copy_done) cudaEventDestroy(copy_done);
+    if (aux_stream) {
+      cudaStreamSynchronize(aux_stream);
+      cudaStreamDestroy(aux_stream);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (int r = 0; r < 3; ++r) {
       if (pd_ev[r]) cudaEventDestroy(pd_ev[r]);
       for (int c = 0; c < 2; ++c)
@@ -587,6 +602,15 @@ struct PlanT : PlanBase {
     if ((rc = dalloc((void**)&Dline, sizeof(cpx<T>) * (size_t)nl))) return rc;
     GGP_CUDA(cudaMemcpy(Dperp, hp.data(), sizeof(cpx<T>) * (size_t)np, cudaMemcpyHostToDevice));
     GGP_CUDA(cudaMemcpy(Dline, hl.data(), sizeof(cpx<T>) * (size_t)nl, cudaMemcpyHostToDevice));
+    if (q6 && sizeof(T) == 4) {
+      std::vector<double2> qp((size_t)np), ql((size_t)nl);
+      for (long long q = 0; q < np; ++q) qp[(size_t)q] = make_double2(perp[(size_t)q].real() * sc, perp[(size_t)q].imag() * sc);
+      for (long long l = 0; l < nl; ++l) ql[(size_t)l] = make_double2(line[(size_t)l].real(), line[(size_t)l].imag());
+      if ((rc = dalloc((void**)&Dq[0], sizeof(double2) * (size_t)np))) return rc;
+      if ((rc = dalloc((void**)&Dq[1], sizeof(double2) * (size_t)nl))) return rc;
+      GGP_CUDA(cudaMemcpy(Dq[0], qp.data(), sizeof(double2) * (size_t)np, cudaMemcpyHostToDevice));
+      GGP_CUDA(cudaMemcpy(Dq[1], ql.data(), sizeof(double2) * (size_t)nl, cudaMemcpyHostToDevice));
+    }
     if constexpr (TwT<T>::split) {
       std::vector<typename TwT<T>::type> sp((size_t)np), sl((size_t)nl);
       for (long long q = 0; q < np; ++q)
@@ -637,6 +661,36 @@ struct PlanT : PlanBase {
     return upload_sep(perp, line);
   }
 
+  // twiddle table of one axis for a radix schedule of E elements per thread: per-pass coalesced blocks (fft_line.cuh),
+  // then, for long lines, the compact tables of the factorised twiddles
+  static void build_twiddles(long long N, long long E, std::vector<typename TwT<T>::type>& h) {
+    const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (long long NS = 1; NS < N;) {
+      const long long R = (N / NS >= E) ? E : N / NS;
+      if (NS > 1)
+        for (long long r = 1; r < R; ++r)
+          for (long long k = 0; k < NS; ++k) {
+            const long double ang = -twopi * (long double)(r * k) / (long double)(NS * R);
+            h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
+          }
+      NS *= R;
+    }
+    if (h.empty()) h.push_back(TwT<T>::make(1.0L, 0.0L));
+    // long lines: compact tables of the factorised twiddles behind the pass blocks (fft_line.cuh, FACT):
+    // [pad to an even count | B[j] = w_N^j, j < 64 | A[j] = w_N^(64 j), j < N/64]
+    if (N >= 4096 && !TwT<T>::split) {
+      if (h.size() % 2) h.push_back(TwT<T>::make(1.0L, 0.0L));
+      for (long long j = 0; j < TWF_LO; ++j) {
+        const long double ang = -twopi * (long double)j / (long double)N;
+        h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
+      }
+      for (long long j = 0; j < N / TWF_LO; ++j) {
+        const long double ang = -twopi * (long double)(j * TWF_LO) / (long double)N;
+        h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
+      }
+    }
+  }
+
   static int ncols_of(int kind, int M) {
     return kind == GGP_TABLE_SCALAR ? 1 : kind == GGP_TABLE_DIAG ? M : kind == GGP_TABLE_FULL ? M * M : 0;
   }
@@ -654,6 +708,7 @@ struct PlanT : PlanBase {
     batch_offset = d.batch_offset;
     dt = d.dt;
     dkind = d.disp_kind;
+    q6 = d.mixed_precision_tables != 0 && d.table_precision == GGP_C128 && sizeof(T) == 4;
     if (d.slab_nranks > 1) {
       if (ndim != 3 || nbatch != 1) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid without batch dims");
       if (d.noise_kind != GGP_NOISE_NONE) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition with noise is not supported yet");
@@ -715,6 +770,21 @@ struct PlanT : PlanBase {
       // (slab: the table arrives in the y-slab layout (n1, n2loc, n3g); same number of points as the z-slab)
       if ((rc = upload_table(d.disp_table, d.table_precision, ncols_of(dkind, M), 1.0 / ((double)nspatial * P), D))) return rc;
       if ((rc = detect_separable(d))) return rc;
+      if (ndim >= 2 && M == 2 && (dkind == GGP_TABLE_DIAG || dkind == GGP_TABLE_FULL) && !getenv("GGP_NO_DAOS")) {
+        // the same table point-major for the strided kernels (see StrParams::Daos)
+        dcols = ncols_of(dkind, M);
+        const double sc = 1.0 / ((double)nspatial * P);
+        std::vector<cpx<T>> tmp((size_t)nspatial * dcols);
+        for (size_t i = 0; i < tmp.size(); ++i) {
+          std::complex<double> z;
+          if (d.table_precision == GGP_C128) z = ((const std::complex<double>*)d.disp_table)[i];
+          else { const std::complex<float> f = ((const std::complex<float>*)d.disp_table)[i]; z = std::complex<double>(f.real(), f.imag()); }
+          z *= sc;
+          tmp[i] = mk<T>((T)z.real(), (T)z.imag());
+        }
+        if ((rc = dalloc((void**)&Daos, sizeof(cpx<T>) * tmp.size()))) return rc;
+        GGP_CUDA(cudaMemcpy(Daos, tmp.data(), sizeof(cpx<T>) * tmp.size(), cudaMemcpyHostToDevice));
+      }
     }
     {
       for (int a = 0; a < ndim; ++a) {
@@ -730,31 +800,7 @@ struct PlanT : PlanBase {
         {
           const long long N = na;
           const long long E = default_E<T>((int)N);
-          const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
-          for (long long NS = 1; NS < N;) {
-            const long long R = (N / NS >= E) ? E : N / NS;
-            if (NS > 1)
-              for (long long r = 1; r < R; ++r)
-                for (long long k = 0; k < NS; ++k) {
-                  const long double ang = -twopi * (long double)(r * k) / (long double)(NS * R);
-                  h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
-                }
-            NS *= R;
-          }
-          if (h.empty()) h.push_back(TwT<T>::make(1.0L, 0.0L));
-          // long lines: compact tables of the factorised twiddles behind the pass blocks (fft_line.cuh, FACT):
-          // [pad to an even count | B[j] = w_N^j, j < 64 | A[j] = w_N^(64 j), j < N/64]
-          if (N >= 4096 && !TwT<T>::split) {
-            if (h.size() % 2) h.push_back(TwT<T>::make(1.0L, 0.0L));
-            for (long long j = 0; j < TWF_LO; ++j) {
-              const long double ang = -twopi * (long double)j / (long double)N;
-              h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
-            }
-            for (long long j = 0; j < N / TWF_LO; ++j) {
-              const long double ang = -twopi * (long double)(j * TWF_LO) / (long double)N;
-              h.push_back(TwT<T>::make(cosl(ang), sinl(ang)));
-            }
-          }
+          build_twiddles(N, E, h);
         }
         if ((rc = dalloc((void**)&tw[a], sizeof(h[0]) * h.size()))) return rc;
         GGP_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice));
@@ -887,6 +933,15 @@ struct PlanT : PlanBase {
       pw.elem_offset = batch_offset * nspatial;
     }
     has_pointwise = pw.vkind || pw.pump || pw.nl || pw.noise;
+    {
+      const int eo = size_supported(n[0]) ? row_E_of<T>((int)n[0], M, pw_variant()) : 0;
+      if (eo > 0 && eo != default_E<T>((int)n[0])) {
+        std::vector<typename TwT<T>::type> h;
+        build_twiddles(n[0], eo, h);
+        if ((rc = dalloc((void**)&tw_row, sizeof(h[0]) * h.size()))) return rc;
+        GGP_CUDA(cudaMemcpy(tw_row, h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice));
+      }
+    }
     if ((rc = setup_tma())) return rc;
     if ((rc = dalloc((void**)&obs_dev, sizeof(double) * (size_t)(nspatial * M + 8)))) return rc;
     GGP_CUDA(cudaStreamSynchronize(stream));
@@ -1136,14 +1191,21 @@ struct PlanT : PlanBase {
     return 0;
   }
 
-  int run_row(bool pre, bool post, const HalfStep<T>& hA, const HalfStep<T>& hB) {
+  // zc0 / zcn: chunk of the local z-planes (slab plans, see slab_iry); zcn < 0: everything.  st: launch stream.
+  int run_row(bool pre, bool post, const HalfStep<T>& hA, const HalfStep<T>& hB, long long zc0 = 0, long long zcn = -1,
+              cudaStream_t st = nullptr) {
+    if (!st) st = stream;
     RowParams<T> p;
     memset(&p, 0, sizeof(p));
     p.u[0] = u[0];
     p.u[1] = u[1];
-    p.tw = tw[0];
+    p.tw = tw_row ? tw_row : tw[0];
     p.nlines = (nspatial / n[0]) * nbatch;
     p.lines_per_image = nspatial / n[0];
+    if (zcn >= 0) {
+      p.line0 = zc0 * n[1];
+      p.nlines = zcn * n[1];
+    }
     p.pw = pw;
     p.hs[0] = hA;
     p.hs[1] = hB;
@@ -1162,7 +1224,7 @@ struct PlanT : PlanBase {
       }
     }
 #endif
-    GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pw_variant(), p, stream), "row_kernel");
+    GGP_LAUNCH(dispatch_row<T>((int)n[0], M, pw_variant(), p, st), "row_kernel");
     ++launches;
     return prof_end();
   }
@@ -1170,7 +1232,9 @@ struct PlanT : PlanBase {
   // strided pass along axis `ax` (1 or 2).  yslab: operate on xbuf in the transposed (n1, n2loc, n3g) layout.
   // scatter: 0 in place; 1 = y pass of the z-slab, results into the y-slabs (xbuf) of their owners; 2 = z pass of
   // the y-slab, results into the z-slabs (u) of their owners (fused all-to-all transpose over peer memory).
-  int run_str(int ax, int mode, bool yslab = false, int scatter = 0) {
+  int run_str(int ax, int mode, bool yslab = false, int scatter = 0, long long zc0 = 0, long long zcn = -1,
+              cudaStream_t st = nullptr) {
+    if (!st) st = stream;
     StrParams<T> p;
     memset(&p, 0, sizeof(p));
     const long long g0 = n[0], g1 = yslab ? n2loc : n[1], g2 = yslab ? n3g : n[2];
@@ -1178,12 +1242,16 @@ struct PlanT : PlanBase {
     p.u[1] = yslab ? xbuf[1] : u[1];
     p.tw = tw[ax];
     for (int i = 0; i < 4; ++i) p.D[i] = D[i];
+    p.Daos = Daos;
+    p.dcols = dcols;
     p.dkind = dkind;
     if (sep && mode == 1) {
       p.D[0] = Dperp;
       p.D[1] = Dline;
       p.Dsp[0] = Dsp[0];
       p.Dsp[1] = Dsp[1];
+      p.Dq[0] = Dq[0];
+      p.Dq[1] = Dq[1];
       p.dkind = KIND_SEP;
     }
     p.mode = mode;
@@ -1222,6 +1290,15 @@ struct PlanT : PlanBase {
         p.dst_base = n[0] * (long long)prank * n2loc;
       }
       p.dst_s2 = 0;
+    }
+    if (zcn >= 0) {
+      // chunk of the z-planes of the z-slab (y passes only): same kernel on a sub-range of the slowest axis
+      if (ax != 1 || yslab) return fail(GGP_ERR_INVALID, "z-plane chunks apply to the y passes of the z-slab");
+      for (int c = 0; c < M; ++c) p.u[c] += zc0 * p.s1;
+      p.no1 = zcn;
+      nother = zcn * nbatch;
+      if (scatter) p.dst_base += zc0 * p.dst_s1;
+      if (scatter && slab_yocc1) p.occ1 = 1;
     }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
@@ -1266,9 +1343,41 @@ struct PlanT : PlanBase {
       }
     }
 #endif
-    GGP_LAUNCH(dispatch_str<T>(N, M, p, g0, nother, stream), "str_kernel");
+    GGP_LAUNCH(dispatch_str<T>(N, M, p, g0, nother, st), "str_kernel");
     ++launches;
     return prof_end();
+  }
+
+  // Slab plans, fused transposes: the local part of a step -- [inverse y pass of step s-1] -> contiguous-axis kernel ->
+  // [forward y pass of step s, its results stored straight into the peers' y-slabs over NVLink] -- touches every
+  // z-plane independently, so it runs in `slab_chunks` chunks of planes alternating between two streams: while one
+  // chunk's forward pass is bound by its NVLink stores, the next chunk's local kernels (HBM-bound) run beside it.
+  int slab_iry(bool do_inv, bool pre, bool post, const HalfStep<T>& hA, const HalfStep<T>& hB, bool do_y) {
+    int rc;
+    int C = (profiling || flush_buf) ? 1 : slab_chunks;
+    if (C > n3loc) C = (int)n3loc;
+    if (C < 1) C = 1;
+    if (C > 1) {
+      if (!aux_stream) {
+        GGP_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+        GGP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        GGP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+      GGP_CUDA(cudaEventRecord(ev_fork, stream));
+      GGP_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+    }
+    for (int c = 0; c < C; ++c) {
+      cudaStream_t st = (c & 1) ? aux_stream : stream;
+      const long long z0 = (long long)c * n3loc / C, z1 = (long long)(c + 1) * n3loc / C;
+      if (do_inv && (rc = run_str(1, 2, false, 0, z0, z1 - z0, st))) return rc;
+      if ((rc = run_row(pre, post, hA, hB, z0, z1 - z0, st))) return rc;
+      if (do_y && (rc = run_str(1, 0, false, 1, z0, z1 - z0, st))) return rc;
+    }
+    if (C > 1) {
+      GGP_CUDA(cudaEventRecord(ev_join, aux_stream));
+      GGP_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    }
+    return 0;
   }
 
   // All-to-all transposes of the slab decomposition (ncclSend/ncclRecv group on the plan's stream).
@@ -1390,6 +1499,8 @@ struct PlanT : PlanBase {
       peer_flags[q] = (unsigned*)ptrs[4];
     }
     p2p = getenv("GGP_SLAB_NCCL") == nullptr;
+    if (const char* e = getenv("GGP_SLAB_CHUNKS")) slab_chunks = atoi(e) > 0 ? atoi(e) : 1;
+    slab_yocc1 = getenv("GGP_SLAB_YOCC1") != nullptr;
     return 0;
   }
   int barrier_status() {
@@ -1400,7 +1511,8 @@ struct PlanT : PlanBase {
 
   // which compile-time variant of the half-step covers this problem (pointwise.cuh)
   int pw_variant() const {
-    if (pw.noise) return pw.noise_field ? PW_FIELD : PW_STOCH;
+    if (pw.noise) return (pw.noise_field || pw.pump_dense) ? PW_FIELD : PW_STOCH;
+    if (pw.pump_dense) return PW_DENSE;
     if (pw.vkind || pw.pump || pw.nl != 1) return PW_DET;
     return PW_KERR;
   }
@@ -1503,6 +1615,18 @@ struct PlanT : PlanBase {
         }
         continue;
       }
+      if (slab && p2p) {
+        // [inverse y pass of step s-1] -> contiguous-axis kernel -> forward y pass + scatter, chunked over z-planes
+        if ((rc = slab_iry(s > 0, s > 0, true, prev2, h1, true))) return rc;
+        if (s > 0 && (rc = window_end())) return rc;
+        if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
+        if ((rc = next_half(s, 1, 1, &prev2))) return rc;
+        if ((rc = window_begin())) return rc;
+        if ((rc = slab_barrier())) return rc;
+        if ((rc = run_str(2, 1, true, 2))) return rc;
+        if ((rc = slab_barrier())) return rc;
+        continue;
+      }
       if ((rc = run_row(s > 0, true, prev2, h1))) return rc;
       if (s > 0 && (rc = window_end())) return rc;     // closes the window of step s-1
       if (noise && (rc = upload_noise(noise, s, 1, 1))) return rc;
@@ -1514,12 +1638,6 @@ struct PlanT : PlanBase {
         if ((rc = run_str(1, 0))) return rc;
         if ((rc = run_str(2, 1))) return rc;
         if ((rc = run_str(1, 2))) return rc;
-      } else if (p2p) {
-        if ((rc = run_str(1, 0, false, 1))) return rc;
-        if ((rc = slab_barrier())) return rc;
-        if ((rc = run_str(2, 1, true, 2))) return rc;
-        if ((rc = slab_barrier())) return rc;
-        if ((rc = run_str(1, 2))) return rc;
       } else {
         if ((rc = run_str(1, 0))) return rc;
         if ((rc = transpose(true))) return rc;
@@ -1529,7 +1647,9 @@ struct PlanT : PlanBase {
       }
     }
     if (dkind != GGP_TABLE_NONE) {
-      if ((rc = run_row(true, false, prev2, none))) return rc;
+      if (slab && p2p) {
+        if ((rc = slab_iry(true, true, false, prev2, none, false))) return rc;
+      } else if ((rc = run_row(true, false, prev2, none))) return rc;
       if ((rc = window_end())) return rc;
     }
     return 0;

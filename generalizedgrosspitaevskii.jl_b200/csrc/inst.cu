@@ -105,7 +105,7 @@ static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t 
 
 template <typename T, int N, int M, int PWV>
 static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
-  using K = KCfg<T, N>;
+  using K = KCfg<T, N, row_E<T>(N, M, PWV)>;
   const size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
   const unsigned grid = (unsigned)((p.nlines + K::LPC - 1) / K::LPC);
   auto k = row_kernel<T, N, M, PWV>;
@@ -122,6 +122,7 @@ static int launch_row_m(int pwv, const RowParams<T>& p, cudaStream_t st) {
   if (pwv == PW_KERR) return launch_row_mp<T, N, M, PW_KERR>(p, st);
   if (pwv == PW_DET) return launch_row_mp<T, N, M, PW_DET>(p, st);
   if (pwv == PW_STOCH) return launch_row_mp<T, N, M, PW_STOCH>(p, st);
+  if (pwv == PW_DENSE) return launch_row_mp<T, N, M, PW_DENSE>(p, st);
   return launch_row_mp<T, N, M, PW_FIELD>(p, st);
 }
 
@@ -234,7 +235,8 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
       smem = with_dl;
     }
   }
-  if (!K::USES_SMEM) p.tma = 0;
+  if (p.occ1 && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;   // more than half an SM's shared memory: one CTA per SM
+  if (!K::USES_SMEM || K::str_parked(M)) p.tma = 0;   // (parked two-component path: plain loads, see KCfg::str_parked)
   if (p.tma) {
     smem = (smem + 15) & ~(size_t)15;
     p.mbar_off = (int)smem;
@@ -285,6 +287,7 @@ static int launch_oned_m(int pwv, const OneDParams<T>& p, cudaStream_t st) {
   if (pwv == PW_KERR) return launch_oned_mp<T, N, M, PW_KERR>(p, st);
   if (pwv == PW_DET) return launch_oned_mp<T, N, M, PW_DET>(p, st);
   if (pwv == PW_STOCH) return launch_oned_mp<T, N, M, PW_STOCH>(p, st);
+  if (pwv == PW_DENSE) return launch_oned_mp<T, N, M, PW_DENSE>(p, st);
   return launch_oned_mp<T, N, M, PW_FIELD>(p, st);
 }
 

@@ -25,6 +25,9 @@
 #ifndef GGP_STOCH_BUDGET
 #define GGP_STOCH_BUDGET 128
 #endif
+#ifndef GGP_DBATCH
+#define GGP_DBATCH 2
+#endif
 #ifndef GGP_STR_D2_BLOCKS
 #define GGP_STR_D2_BLOCKS 2
 #endif
@@ -35,7 +38,8 @@ template <typename T>
 struct RowParams {
   cpx<T>* u[2];
   const typename TwT<T>::type* tw;
-  long long nlines;           // (nspatial / N) * nbatch
+  long long nlines;           // (nspatial / N) * nbatch  (or the lines of one chunk of them)
+  long long line0;            // first line of this launch (chunked launches of slab plans; 0 otherwise)
   long long lines_per_image;  // nspatial / N ; spatial table line = line % lines_per_image
   PointwiseParams<T> pw;
   HalfStep<T> hs[2];  // trailing half-step of step n, leading half-step of step n+1
@@ -76,6 +80,16 @@ struct alignas(64) StrParams {
   int slab;     // slab-decomposed plan (LDG loads, peer stores): the launcher picks 128-byte tiles
   int pf_dist;  // > 0: while waiting for its own tile a CTA prefetches tile (blockIdx + pf_dist) into L2 -- set by the
                 // launcher to the number of resident CTAs when the state does not fit the L2 (see str_kernel)
+  // two-component diagonal / matrix tables, array-of-structs as the host lays them out ([point][entry], entries
+  // column-major m11 m21 m12 m22): one tile row reads W * dcols contiguous complex numbers (128 B for W = 2 fp64 matrix
+  // entries) instead of a 32-byte piece from each of four planes a full array apart.  The strided kernel of a state
+  // that does not fit the L2 next to its table (C3: 32 MB + 64 MB + pump) was DRAM-bound on those pieces at
+  // 1.4 TB/s -- every piece its own DRAM page (ncu r02h).  Daos == nullptr: planes D[].
+  const cpx<T>* Daos;
+  int dcols;
+  const double2* Dq[2];  // quirk Q6 (ggp_desc.mixed_precision_tables): Float64 copies of (D_perp, D_line) of a ComplexF32 plan
+  int occ1;     // launcher hint: keep this grid at ONE CTA per SM (an NVLink-bound scatter pass of a slab plan that shares
+                // the SMs with the next chunk's local kernels on a second stream, see slab_iry in ggp_api.cu)
   int tw_smem;  // twiddle table staged in shared memory although the compile-time default (str_tw_smem) says no:
                 // set by the launcher when the geometry chosen at run time (W, CTAs per SM) leaves room for it
 };
@@ -92,9 +106,22 @@ struct OneDParams {
   int dkind;
 };
 
-template <typename T, int N>
+// elements per thread of the row kernel where it differs from the default: the stochastic fp64 kernel on short lines is
+// bound by fixed-latency chains (Philox rounds, polynomial sincos, DFMA) at 16 warps per SM with radix 8 / 128 registers;
+// radix 4 fits 64 registers = 32 warps per SM (C4, 256^2 x 1024 trajectories: row kernel 1.56 -> 1.34 ms).  The strided
+// kernel keeps radix 8 (it is near its HBM time there and one more pass costs more than the warps gain: 0.54 -> 0.73 ms).
+template <typename T>
+__host__ __device__ constexpr int row_E(int N, int M, int pwv) {
+#ifdef GGP_NO_ROW_E4
+  return 0;
+#else
+  return (sizeof(T) == 8 && pw_is_stoch(pwv) && M == 1 && N >= 64 && N <= 256) ? 4 : 0;
+#endif
+}
+
+template <typename T, int N, int EO = 0>
 struct KCfg {
-  using L = LineCfg<T, N>;
+  using L = LineCfg<T, N, EO>;
   static constexpr int E = L::E;
   static constexpr int TPL = L::TPL;
   static constexpr int G = 128 / (int)sizeof(cpx<T>);  // lanes served by one shared-memory wavefront
@@ -125,7 +152,23 @@ struct KCfg {
   // registers: with at most 32 words of field data per thread the kernels fit 64 registers, and the launch
   // bounds ask for as many CTAs per SM as that allows; wider data (M = 2, long fp64 lines) takes what it needs
   __host__ __device__ static constexpr int data_regs(int M) { return M * E * (int)sizeof(cpx<T>) / 4; }
+  // Two components in the strided kernel: ONE component in registers at a time, the other parked in its (otherwise
+  // idle) exchange line -- as in the row kernel (row_parked_body).  With both components in registers the kernel needs
+  // 64 data registers + the exp_D entries: the fp32 instantiation took 242 registers = ONE 8-warp CTA per SM (C3 in
+  // ComplexF32: 57 us per launch).  Parked: 32 data registers, ~120 in all, two CTAs per SM, table loads batched
+  // (37 us).  (No TMA staging on this path: the dense tile of
+  // component 1 would overlap the exchange lines component 0 is transformed in.)
+  __host__ __device__ static constexpr bool str_parked(int M) {
+#ifdef GGP_NO_STR_PARK
+    return false;
+#else
+    // fp32 only: for fp64 the parked and the two-components-in-registers kernels measured the same (C3: 72.5 vs
+    // 71.8 us per launch, A/B r02j), and the latter keeps its TMA staging
+    return M == 2 && USES_SMEM && sizeof(T) == 4 && data_regs(1) <= 32;
+#endif
+  }
   __host__ __device__ static constexpr int str_min_blocks(int M) {
+    if (str_parked(M)) return 1024 / STR_THREADS >= 2 ? 2 : 1;
     // two-component fp64 tiles (64 data registers, 256 threads): left alone the compiler takes 206 registers = ONE
     // 8-warp CTA per SM (C3, ncu r01t: issue-active 11.5 %); capped at 128 two CTAs fit
     if (sizeof(T) == 8 && data_regs(M) == 64 && STR_THREADS <= 256) return GGP_STR_D2_BLOCKS;
@@ -186,7 +229,7 @@ struct KCfg {
       return bp < 1 ? 1 : bp;
     }
     const int dr = data_regs(M);
-    const int budget = dr <= 32 ? (pw_is_stoch(pwv) ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pw_is_stoch(pwv) ? 255 : 168) : 255);
+    const int budget = dr <= 32 ? ((pw_is_stoch(pwv) && EO == 0) ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pw_is_stoch(pwv) ? 255 : 168) : 255);
     const int b = 65536 / (ROW_THREADS * budget);
     return b < 1 ? 1 : b;
   }
@@ -203,23 +246,23 @@ __device__ __forceinline__ void conj_all(cpx<T> (&v)[E]) {
 // on conjugated data (ifft(x) = conj(fft(conj(x)))), selected by a loop that is NOT unrolled.
 // This halves the instruction footprint -- the first version of these kernels was bound by
 // instruction-cache misses (ncu: stall_no_instructions dominant, profiles/r01_notes.md).
-template <typename T, int N, int M, typename SYNC, bool FACT = false>
-__device__ __forceinline__ void fft_fwd_all(cpx<T> (&v)[M][LineCfg<T, N>::E], const int t, cpx<T>* sl, const int LS,
+template <typename T, int N, int M, typename SYNC, bool FACT = false, int EO = 0>
+__device__ __forceinline__ void fft_fwd_all(cpx<T> (&v)[M][LineCfg<T, N, EO>::E], const int t, cpx<T>* sl, const int LS,
                                             const typename TwT<T>::type* __restrict__ tw, const bool inverse,
                                             const typename TwT<T>::type* __restrict__ twc = nullptr) {
 #pragma unroll
   for (int c = 0; c < M; ++c) {
-    if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
-    fft_line<T, N, -1, SYNC, true, FACT>(v[c], t, sl + c * LS, tw, twc);
-    if (inverse) conj_all<T, LineCfg<T, N>::E>(v[c]);
+    if (inverse) conj_all<T, LineCfg<T, N, EO>::E>(v[c]);
+    fft_line<T, N, -1, SYNC, true, FACT, EO>(v[c], t, sl + c * LS, tw, twc);
+    if (inverse) conj_all<T, LineCfg<T, N, EO>::E>(v[c]);
   }
 }
 
-template <typename T, int N, int M, int PWV>
-__device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N>::E], const PointwiseParams<T>& pw,
+template <typename T, int N, int M, int PWV, int EO = 0>
+__device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N, EO>::E], const PointwiseParams<T>& pw,
                                            const HalfStep<T>* hs, const int nh, const long long sidx0,
                                            const long long gidx0, const long long stride) {
-  constexpr int E = LineCfg<T, N>::E;
+  constexpr int E = LineCfg<T, N, EO>::E;
   if constexpr (pw_is_stoch(PWV)) {
     // All Philox words of this thread first (E*M independent chains: good ILP), one call per element and
     // component serving both half-steps of the pair; then the half-steps as in the deterministic variant.
@@ -359,16 +402,19 @@ __device__ __forceinline__ void row_parked_body(const RowParams<T>& p, cpx<T>* s
 
 // flags: bit 0 = PRE (inverse FFT_x before the half-steps), bit 1 = POST (forward FFT_x after)
 template <typename T, int N, int M, int PWV>
-__global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_blocks(M, PWV)) row_kernel(const RowParams<T> p) {
-  using K = KCfg<T, N>;
+__global__ void __launch_bounds__(KCfg<T, N, row_E<T>(N, M, PWV)>::ROW_THREADS, KCfg<T, N, row_E<T>(N, M, PWV)>::row_min_blocks(M, PWV))
+    row_kernel(const RowParams<T> p) {
+  constexpr int EO = row_E<T>(N, M, PWV);
+  using K = KCfg<T, N, EO>;
   constexpr int E = K::E, TPL = K::TPL, LPC = K::LPC, LS = K::row_ls();
   using SYNC = typename K::RowSync;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx<T>* smem = reinterpret_cast<cpx<T>*>(smem_raw);
 
   const int grp = threadIdx.x / TPL, t = threadIdx.x % TPL;
-  const long long line = (long long)blockIdx.x * LPC + grp;
-  const bool active = line < p.nlines;
+  const long long lrel = (long long)blockIdx.x * LPC + grp;
+  const long long line = lrel + p.line0;
+  const bool active = lrel < p.nlines;
   const long long goff = line * N + t;
   const long long soff = (line % p.lines_per_image) * N + t;
   cpx<T>* sl = smem + (size_t)grp * M * LS;
@@ -387,8 +433,8 @@ __global__ void __launch_bounds__(KCfg<T, N>::ROW_THREADS, KCfg<T, N>::row_min_b
 
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-      if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC>(v, t, sl, LS, p.tw, it == 0);
-      if (it == 0 && active) half_steps<T, N, M, PWV>(v, p.pw, p.hs, 2, soff, goff, TPL);
+      if (p.flags & (1 << it)) fft_fwd_all<T, N, M, SYNC, false, EO>(v, t, sl, LS, p.tw, it == 0);
+      if (it == 0 && active) half_steps<T, N, M, PWV, EO>(v, p.pw, p.hs, 2, soff, goff, TPL);
       if (it == 0 && p.pdl_pos == 2) pdl_launch_dependents();
     }
     if (p.pdl_pos == 3) pdl_launch_dependents();
@@ -476,6 +522,128 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   }
   if (p.pdl_pos == 0) pdl_launch_dependents();
   pdl_wait();
+  if constexpr (K::str_parked(M)) {
+    // ---- two components, one in registers at a time (see KCfg::str_parked) ----
+    cpx<T> a[E];
+    const bool sepq = sep;
+    auto store = [&](const int c) {
+      if (p.scatter) {
+        const long long dbase = p.dst_base + xt * W + xw + o1 * p.dst_s1 + o2 * p.dst_s2;
+        const int mask = (1 << p.dst_shift) - 1;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int j = t + m * TPL;
+          p.dst[j >> p.dst_shift][c][dbase + (long long)(j & mask) * p.dst_ls] = a[m];
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) p.u[c][off + m * mstride] = a[m];
+      }
+    };
+    if (tws || (sepq && p.dl_smem)) asm volatile("cp.async.wait_all;" ::: "memory");  // published by the transform's barriers
+    if (p.mode != 1) {
+      // forward-only / inverse-only (middle axis of a 3-D grid): the components are independent
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = p.u[c][off + m * mstride];
+        if (p.mode == 2) conj_all<T, E>(a);
+        fft_line<T, N, -1, SyncBlock, true, K::FACT>(a, t, sl + c * LS, twp, twc);
+        if (p.mode == 2) conj_all<T, E>(a);
+        if (c == 0 && p.pdl_pos == 2) pdl_launch_dependents();
+        if (c == 1 && p.pdl_pos == 3) pdl_launch_dependents();
+        store(c);
+      }
+      return;
+    }
+    using L = LineCfg<T, N>;
+    constexpr bool LIN = (TPL % E == 0);               // pad(t + m*TPL) = pad(t) + m*(TPL + TPL/E)
+    cpx<T>* const park = sl + L::pad(t);               // component 0's line; every thread parks and reloads ITS OWN elements
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) a[m] = p.u[c][off + m * mstride];
+      fft_line<T, N, -1, SyncBlock, true, K::FACT>(a, t, sl + c * LS, twp, twc);
+      if (c == 0) {
+        __syncthreads();                               // the last pass may still be reading this line
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          if constexpr (LIN) park[m * (TPL + TPL / E)] = a[m];
+          else sl[L::pad(t + m * TPL)] = a[m];
+        }
+      }
+    }
+    if (p.pdl_pos == 1 || p.pdl_pos == 2) pdl_launch_dependents();
+    // k-space multiply  u~ <- exp_D[k] (x) u~  on both components of a point
+    if (sepq) {
+      const cpx<T>* dline = p.dl_smem ? (sdl + t) : (p.D[1] + t);
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        cpx<T> f0;
+        if constexpr (LIN) f0 = park[m * (TPL + TPL / E)];
+        else f0 = sl[L::pad(t + m * TPL)];
+        const cpx<T> d = cmul(dperp, dline[m * TPL]);
+        f0 = cmul(d, f0);
+        a[m] = cmul(d, a[m]);
+        if constexpr (LIN) park[m * (TPL + TPL / E)] = f0;
+        else sl[L::pad(t + m * TPL)] = f0;
+      }
+    } else {
+      // full tables: the entries of DB elements are requested together (ldg_nc_ordered) -- left to the scheduler they
+      // are loaded one element at a time, E dependent round trips to L2 / DRAM per thread (ncu r02h)
+      constexpr int DB = GGP_DBATCH < E ? GGP_DBATCH : E;
+      const int npl = p.dkind == KIND_SCALAR ? 1 : (p.dkind == KIND_DIAG ? 2 : 4);
+#pragma unroll
+      for (int m0 = 0; m0 < E; m0 += DB) {
+        cpx<T> d[DB][4];
+#pragma unroll
+        for (int b = 0; b < DB; ++b)
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl)
+            if (pl < npl)
+              d[b][pl] = p.Daos ? ldg_nc_ordered(p.Daos + (toff + (m0 + b) * mstride) * p.dcols + pl)
+                                : ldg_nc_ordered(p.D[pl] + toff + (m0 + b) * mstride);
+#pragma unroll
+        for (int b = 0; b < DB; ++b) {
+          const int m = m0 + b;
+          cpx<T> f0, f1 = a[m];
+          if constexpr (LIN) f0 = park[m * (TPL + TPL / E)];
+          else f0 = sl[L::pad(t + m * TPL)];
+          if (p.dkind == KIND_FULL) {               // planes [col * 2 + row]
+            const cpx<T> r0 = cmul(d[b][0], f0) + cmul(d[b][2], f1);
+            const cpx<T> r1 = cmul(d[b][1], f0) + cmul(d[b][3], f1);
+            f0 = r0;
+            f1 = r1;
+          } else if (p.dkind == KIND_DIAG) {
+            f0 = cmul(d[b][0], f0);
+            f1 = cmul(d[b][1], f1);
+          } else {
+            f0 = cmul(d[b][0], f0);
+            f1 = cmul(d[b][0], f1);
+          }
+          if constexpr (LIN) park[m * (TPL + TPL / E)] = f0;
+          else sl[L::pad(t + m * TPL)] = f0;
+          a[m] = f1;
+        }
+      }
+    }
+#pragma unroll 1
+    for (int c = 1; c >= 0; --c) {
+      if (c == 0) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          if constexpr (LIN) a[m] = park[m * (TPL + TPL / E)];
+          else a[m] = sl[L::pad(t + m * TPL)];
+        }
+      }
+      conj_all<T, E>(a);
+      fft_line<T, N, -1, SyncBlock, true, K::FACT>(a, t, sl + c * LS, twp, twc);   // PRESYNC: everybody has reloaded
+      conj_all<T, E>(a);
+      if (c == 0 && p.pdl_pos == 3) pdl_launch_dependents();
+      store(c);
+    }
+    return;
+  }
   cpx<T> v[M][E];
   if (p.tma) {
     // one thread asks the TMA engine for the whole tile, dense [component][row][W] at the start of the
@@ -537,6 +705,22 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
 #pragma unroll
             for (int c = 0; c < M; ++c) v[c][m] = TwT<T>::mul(TwT<T>::mul(v[c][m], dl), dp);
           }
+        } else if (sizeof(T) == 4 && p.Dq[0]) {
+          // quirk Q6: the reference holds a ComplexF64 table for this ComplexF32 problem and forms exp_D[k] * u~[k] in
+          // ComplexF64 before the store rounds it (src/misc.jl:14-17, src/kernels.jl:44-53): same here, on the
+          // otherwise idle fp64 pipe
+          const double2 dp = p.Dq[0][toff - (long long)t * p.ls];
+          const double2* dline = p.Dq[1] + t;
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const double2 dl = dline[m * TPL];
+            const double dre = dp.x * dl.x - dp.y * dl.y, dim = dp.x * dl.y + dp.y * dl.x;
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+              const double vx = (double)v[c][m].x, vy = (double)v[c][m].y;
+              v[c][m] = mk<T>((T)(dre * vx - dim * vy), (T)(dre * vy + dim * vx));
+            }
+          }
         } else if (p.dl_smem) {
           const cpx<T>* dline = sdl + t;
 #pragma unroll
@@ -560,7 +744,13 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
           cpx<T> f[M];
 #pragma unroll
           for (int c = 0; c < M; ++c) f[c] = v[c][m];
-          disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+          if (M == 2 && p.Daos) {
+            const cpx<T>* q = p.Daos + (toff + m * mstride) * p.dcols;
+            const cpx<T>* planes[4] = {q, q + 1, q + 2, q + 3};
+            disp_point<T, M>(f, planes, p.dkind, 0);
+          } else {
+            disp_point<T, M>(f, p.D, p.dkind, toff + m * mstride);
+          }
 #pragma unroll
           for (int c = 0; c < M; ++c) v[c][m] = f[c];
         }
@@ -670,5 +860,8 @@ int launch_oned(int M, int pwv, const OneDParams<T>& p, cudaStream_t st);
 // line stride LS, threads per CTA, and whether the line needs the shared exchange buffer
 template <typename T, int N>
 void str_query(int M, int ax, int slab, long long nfast, int* W, int* LS, int* threads, int* uses_smem);
+// elements per thread (= radix schedule of the twiddle table) the row kernel uses for (N, M, variant); 0: the default
+template <typename T>
+inline int row_E_of(int N, int M, int pwv) { return row_E<T>(N, M, pwv); }
 
 }  // namespace ggp

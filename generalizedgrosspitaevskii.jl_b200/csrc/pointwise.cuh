@@ -41,7 +41,7 @@ struct PointwiseParams {
   int pump_const;      // the pump profile is the same at every grid point (e.g. examples/truncated_wigner.jl:37-39):
   cpx<T> S_const[2];   // its value rides in the parameters and the table is not read
   int pump_zero[2];    // per-component pump (pump == 2): this component's profile is identically zero, skip its loads
-  int pump_dense;      // profiles come from HalfStep::pd_now / pd_next instead of S
+  int pump_dense;      // profiles come from HalfStep::pd_now / pd_next instead of S (variants PW_DENSE / PW_FIELD)
   int nl;      // 0 none, 1 real coefficients, 2 complex coefficients
   T nl_c_re[2], nl_c_im[2];
   T nl_g_re[2][2], nl_g_im[2][2];
@@ -167,8 +167,10 @@ __device__ __forceinline__ cpx<T> normal_from(const uint4 r, uint32_t ctr, int r
 //   PW_STOCH  + position noise (host-fed or Philox), constant amplitude            (C4, windowed FT)
 //   PW_FIELD  + field- / position-dependent noise amplitude (GGP_NOISE_FIELD); its own variant because the extra
 //             live values cost the constant-amplitude kernel 4 % when they shared one (C4: 8.52 -> 8.88 ms/step)
-enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2, PW_FIELD = 3 };
-__host__ __device__ constexpr bool pw_is_stoch(int pwv) { return pwv >= PW_STOCH; }
+//   PW_DENSE  PW_DET + dense time-dependent pump (profiles per half-step, GGP_PUMP_DENSE); with noise: PW_FIELD
+enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2, PW_FIELD = 3, PW_DENSE = 4 };
+__host__ __device__ constexpr bool pw_is_stoch(int pwv) { return pwv == PW_STOCH || pwv == PW_FIELD; }
+__host__ __device__ constexpr bool pw_has_dense(int pwv) { return pwv == PW_DENSE || pwv == PW_FIELD; }
 
 // One real-space half-step at one grid point.  sidx: index into the spatial tables; gidx: local
 // element index (spatial + batch) for noise.
@@ -229,17 +231,17 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
     }
   }
   // w = f + (dt/2) a_now S
-  cpx<T> w[M], sv[M], svn[M];
+  cpx<T> w[M], sv[M];
   if (p.pump) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      if (p.pump_dense) {
+      // dense pump (its own compile-time variants: carried by PW_DET behind a run-time flag the extra route cost the
+      // register-bound two-component row kernels 10 - 22 %, ncu / A-B r02f)
+      if (pw_has_dense(PWV) && p.pump_dense) {
         sv[j] = ((const cpx<T>*)h.pd_now[p.pump == 1 ? 0 : j])[sidx];
-        svn[j] = ((const cpx<T>*)h.pd_next[p.pump == 1 ? 0 : j])[sidx];
       } else {
         sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j]
                              : ((p.pump == 2 && p.pump_zero[j]) ? mk<T>((T)0, (T)0) : p.S[p.pump == 1 ? 0 : j][sidx]);
-        svn[j] = sv[j];
       }
       w[j] = f[j] + cmul(h.fnow, sv[j]);
     }
@@ -269,7 +271,11 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
   }
   if (p.pump) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) res[i] = res[i] + cmul(h.fnext, svn[i]);
+    for (int i = 0; i < M; ++i) {
+      // dense pump: F_next is its own profile, loaded here (no extra live values for the other pump kinds)
+      if (pw_has_dense(PWV) && p.pump_dense) sv[i] = ((const cpx<T>*)h.pd_next[p.pump == 1 ? 0 : i])[sidx];
+      res[i] = res[i] + cmul(h.fnext, sv[i]);
+    }
   }
   if (pw_is_stoch(PWV) && p.noise) {
 #pragma unroll

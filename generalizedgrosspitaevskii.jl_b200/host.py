@@ -727,6 +727,10 @@ class StrangSplittingIterator:
         d.disp_kind, d.pot_kind = dkind, vkind
         if dkind == L.TABLE_SCALAR and dtype == np.complex64 and slab is None and not os.environ.get("GGP_NO_SEP_HINT"):
             d.disp_sep_tol = separable_dispersion_tol(prob.dispersion, rg, prob.param, dtab)
+        # quirk Q6: ComplexF32 fields stepped with a Float64 dt / lengths hold ComplexF64 tables in the reference
+        if dtype == np.complex64 and dtab is not None and np.asarray(dtab).dtype == np.complex128 \
+                and not os.environ.get("GGP_NO_Q6"):
+            d.mixed_precision_tables = 1
         d.disp_table = as_c128(dtab) if dtab is not None else None
         if daxes is not None:
             for a_, ax_ in enumerate(daxes):

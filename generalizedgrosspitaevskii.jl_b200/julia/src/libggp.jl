@@ -49,6 +49,8 @@ struct GgpDesc
     noise_profile::Ptr{Cvoid}        # GGP_NOISE_FIELD: n[1] ComplexF64 values P(point(k1)) or C_NULL (quirk Q2)
     disp_sep_tol::Float64            # 0 = library default; see include/ggp.h (separable dispersion)
     disp_axes::NTuple{3,Ptr{Cvoid}}  # GGP_TABLE_SEP_AXES (ABI 4): per-axis factors of a scalar exp_D, else C_NULL
+    mixed_precision_tables::Int32    # 1: ComplexF32 fields with ComplexF64 tables in the reference (quirk Q6)
+    reserved1::Int32
 end
 
 const _lib = Ref{Ptr{Cvoid}}(C_NULL)

@@ -125,7 +125,8 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
         CT == ComplexF32 ? GGP_C64 : GGP_C128, GGP_C128, Int32(device), Int32(0), C_NULL, Float64(dt),
         dkind, vkind, _ptr(dflat), _ptr(vflat), nl_kind, nl_scalar, nl_c, nl_g,
         pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed, Int32(0), Int32(0),
-        alpha, _ptr(nprof), sep_tol, (Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL)))
+        alpha, _ptr(nprof), sep_tol, (Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL)),
+        Int32(CT == ComplexF32 && exp_D isa AbstractArray && real(eltype(eltype(exp_D))) == Float64), Int32(0))
     handle = GC.@preserve dflat vflat sflat nprof ggp_plan_create(desc)
     ggp_set_state(handle, host_u0)                                                    # u = copy.(prob.u0), :48
 

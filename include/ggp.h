@@ -170,6 +170,15 @@ typedef struct ggp_desc {
      over axes (|k|^2/2 + const ...) this replaces the full-grid table -- 16 GiB of host memory for a 1024^3
      ComplexF64 table -- by d short vectors.  Slab plans pass the GLOBAL axes; the library slices. */
   const void *disp_axes[3];
+
+  /* Mixed-precision tables (ABI 4).  In the reference the table element type follows the user's
+     types (src/misc.jl:14-17): a ComplexF32 problem stepped with a Float64 dt (or Float64 lengths) holds ComplexF64
+     tables and multiplies in ComplexF64 before rounding to ComplexF32 on store (src/kernels.jl:51-53).  1 = this is
+     such a problem: a ComplexF32 plan then keeps the two factors of a separable exp_D in Float64 and forms
+     exp_D[k] * u~[k] in Float64 (one rounding, as the reference); full (non-separable) tables, exp_V and the
+     nonlinear phase stay in the plan's precision (documented deviation).  0 = tables in plan precision. */
+  int32_t mixed_precision_tables;
+  int32_t reserved1;
 } ggp_desc;
 
 typedef struct ggp_plan ggp_plan;

@@ -139,3 +139,37 @@ def test_strided_lines_1024_2048(G, dtype, n2):
     pbg, pbo = (_rect_problem(ns, (n2, 64), dtype, (2.0, 64.0)) for ns in (G, O))
     g, o = solve_gpu(G, pbg), solve_oracle(pbo)
     assert rel_l2(g, o) <= TOL[np.dtype(dtype)]
+
+
+def test_q6_complex64_fields_with_float64_dt(G):
+    """SURVEY quirk Q6 (/root/reference/src/misc.jl:14-17): ComplexF32 fields stepped with Float64 dt / lengths hold
+    ComplexF64 tables in the reference and multiply in ComplexF64 before the store rounds.  The oracle reproduces that
+    by NumPy promotion; the backend keeps Float64 factors of the separable exp_D (ggp_desc.mixed_precision_tables).
+    Both routes are inside the ComplexF32 gate; the Float64 factors must not be further from the oracle than
+    demoted ones."""
+    import os
+
+    def problem(ns):
+        N, L = 512, 64.0
+        rs = np.arange(N) * (L / N)
+        X, Y = np.meshgrid(rs, rs, indexing="xy")
+        rng = np.random.default_rng(4)
+        xi = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))) / np.sqrt(2)
+        u0 = (np.exp(-((X - L / 2) ** 2 + (Y - L / 2) ** 2) / 16) * (1 + 0.1 * xi)).astype(np.complex64)
+        return dict(u0=(u0,), lengths=(L, L),
+                    kwargs=dict(dispersion=lambda ks, p: (ks[0] * ks[0] + ks[1] * ks[1]) / 2,
+                                nonlinearity=lambda u, p: ns.abs2(u[0])),
+                    tspan=(0.0, 0.3), dt=1e-3, nsaves=1)
+
+    o = solve_oracle(problem(O))
+    assert o[0].dtype == np.complex64
+    g_q6 = solve_gpu(G, problem(G))
+    os.environ["GGP_NO_Q6"] = "1"
+    try:
+        g_plain = solve_gpu(G, problem(G))
+    finally:
+        del os.environ["GGP_NO_Q6"]
+    d_q6, d_plain = rel_l2(g_q6, o), rel_l2(g_plain, o)
+    print(f"\nQ6 (c64 fields, Float64 dt, 300 steps at 512^2): Float64 exp_D factors {d_q6:.3e}, demoted {d_plain:.3e}")
+    assert d_q6 <= 1e-4 and d_plain <= 1e-4
+    assert d_q6 <= 1.05 * d_plain

@@ -253,3 +253,36 @@ def test_noise_prototype_shapes_are_checked(G):
                                     noise_prototype=(np.zeros((4, 16)), np.zeros((4, 16), dtype=np.complex128)))
     with pytest.raises(G.UnsupportedForm):
         G.init(prob, G.StrangSplitting(), (0.0, 0.1), dt=0.05, nsaves=1)
+
+
+def test_host_helpers_against_independent_facts(G):
+    """host.py and the oracle restate the same reference lines, so comparing them with each other
+    cannot catch a shared misreading.  Here the host helpers are pinned to facts that do not come from either text:
+    NumPy's own fftfreq (AbstractFFTs uses the same convention, negative Nyquist bin), scipy's matrix exponential, and
+    the dt values the reference's examples resolve to (computed by hand from the Julia expressions)."""
+    import importlib
+    import scipy.linalg
+    host = importlib.import_module("ggp_b200.host")
+    for n, L in [(8, 5.0), (7, 3.0), (64, 20.0), (2, 1.0)]:
+        prob = G.GrossPitaevskiiProblem((np.zeros(n, dtype=np.complex128),), (L,))
+        assert np.allclose(G.reciprocal_grid(prob)[0], 2 * np.pi * np.fft.fftfreq(n, d=L / n), rtol=1e-15, atol=0)
+        assert np.allclose(G.direct_grid(prob)[0], np.arange(n) * L / n, rtol=1e-15, atol=0)
+        if n % 2 == 0:
+            assert G.reciprocal_grid(prob)[0][n // 2] < 0                         # Nyquist bin is negative (Q4)
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        A = rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2))
+        m11, m21, m12, m22 = host._expm2(A[0, 0], A[1, 0], A[0, 1], A[1, 1])
+        assert np.allclose(np.array([[m11, m12], [m21, m22]]), scipy.linalg.expm(A), rtol=1e-12, atol=1e-13)
+    B = np.array([[0.3 - 0.1j, 0.0], [0.0, 0.3 - 0.1j]])                          # vanishing discriminant branch
+    m11, m21, m12, m22 = host._expm2(B[0, 0], B[1, 0], B[0, 1], B[1, 1])
+    assert np.allclose(np.array([[m11, m12], [m21, m22]]), scipy.linalg.expm(B), rtol=1e-13)
+    # Q3: examples/quick_start.jl (dt=0.01, nsaves=64): tspan (0,1) -> 2 steps/save, _dt = 1/128; (0,0.4) -> 1, 0.00625;
+    # test/exciton_polariton_test.jl (dt=0.1, tspan (0,100), nsaves=256) -> 4, 0.09765625; bistability -> 129 steps/save
+    for dt, tspan, ns, sps, want in [(0.01, (0, 1), 64, 2, 1 / 128), (0.01, (0, 0.4), 64, 1, 0.00625),
+                                     (1e-1, (0, 100), 256, 4, 0.09765625), (0.05, (0, 3300), 512, 129, 3300 / 512 / 129)]:
+        got, ts, s = G.resolve_fixed_timestepping(dt, tspan, ns)
+        assert s == sps and got == want and len(ts) == ns + 1 and ts[0] == tspan[0]
+    # cis of a complex argument: exp(-Im) * (cos Re + i sin Re)
+    z = np.array([0.3 - 0.2j, -1.1 + 0.4j])
+    assert np.allclose(host._cis(z), np.exp(1j * z), rtol=1e-15)
