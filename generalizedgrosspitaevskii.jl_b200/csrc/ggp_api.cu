@@ -471,6 +471,12 @@ struct PlanT : PlanBase {
   std::vector<void*> ipc_opened;
   cudaStream_t aux_stream = nullptr;      // second stream of the chunked local phase (slab_iry)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // copy-engine transposes (GGP_SLAB_CE): the scatter passes write a destination-ordered LOCAL staging buffer and the
+  // copy engines push it to the peers while the next chunk computes -- the NVLink time leaves the SMs
+  bool slab_ce = false;
+  cpx<T>* stage[2] = {nullptr, nullptr};
+  cudaStream_t ce_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_chunk[16] = {}, ev_ce[2] = {nullptr, nullptr};
   int slab_chunks = 4;
   bool slab_yocc1 = false;   // GGP_SLAB_YOCC1=1: the chunked scatter pass runs at one CTA per SM (room for the other stream)
   // TMA path of the strided kernel, per strided axis (1, 2)
@@ -499,6 +505,15 @@ struct PlanT : PlanBase {
       cudaStreamSynchronize(aux_stream);
       cudaStreamDestroy(aux_stream);
     }
+    for (int i = 0; i < 2; ++i) {
+      if (ce_stream[i]) {
+        cudaStreamSynchronize(ce_stream[i]);
+        cudaStreamDestroy(ce_stream[i]);
+      }
+      if (ev_ce[i]) cudaEventDestroy(ev_ce[i]);
+    }
+    for (int i = 0; i < 16; ++i)
+      if (ev_chunk[i]) cudaEventDestroy(ev_chunk[i]);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     for (int r = 0; r < 3; ++r) {
@@ -1232,8 +1247,9 @@ struct PlanT : PlanBase {
   // strided pass along axis `ax` (1 or 2).  yslab: operate on xbuf in the transposed (n1, n2loc, n3g) layout.
   // scatter: 0 in place; 1 = y pass of the z-slab, results into the y-slabs (xbuf) of their owners; 2 = z pass of
   // the y-slab, results into the z-slabs (u) of their owners (fused all-to-all transpose over peer memory).
+  // to_stage: the scatter pass writes the local staging buffer (copy-engine transposes) instead of peer memory
   int run_str(int ax, int mode, bool yslab = false, int scatter = 0, long long zc0 = 0, long long zcn = -1,
-              cudaStream_t st = nullptr) {
+              cudaStream_t st = nullptr, bool to_stage = false) {
     if (!st) st = stream;
     StrParams<T> p;
     memset(&p, 0, sizeof(p));
@@ -1290,15 +1306,34 @@ struct PlanT : PlanBase {
         p.dst_base = n[0] * (long long)prank * n2loc;
       }
       p.dst_s2 = 0;
+      if (to_stage) {
+        // destination-ordered staging: block q (n1 * n2loc * n3loc elements) is what rank q receives
+        const long long blk = n[0] * n2loc * n3loc;
+        if (scatter == 1) {
+          // [zl][jl][x], the order of the peer's y-slab restricted to my z-range: same strides, contiguous per peer;
+          // my own block still goes straight into my own xbuf
+          for (int q = 0; q < P; ++q)
+            for (int c = 0; c < M; ++c)
+              if (q != prank) p.dst[q][c] = stage[c] + (long long)q * blk - p.dst_base;
+        } else {
+          // [zl][yl][x] per peer (own block included: it is copied like the others)
+          p.dst_ls = n[0] * n2loc;
+          p.dst_s1 = n[0];
+          p.dst_base = 0;
+          for (int q = 0; q < P; ++q)
+            for (int c = 0; c < M; ++c) p.dst[q][c] = stage[c] + (long long)q * blk;
+        }
+      }
     }
     if (zcn >= 0) {
-      // chunk of the z-planes of the z-slab (y passes only): same kernel on a sub-range of the slowest axis
-      if (ax != 1 || yslab) return fail(GGP_ERR_INVALID, "z-plane chunks apply to the y passes of the z-slab");
+      // chunk of the slowest remaining axis: z-planes of the z-slab (y passes), y-rows of the y-slab (z pass)
+      if ((ax == 1) == yslab) return fail(GGP_ERR_INVALID, "chunks apply to the y passes of the z-slab and the z pass of the y-slab");
       for (int c = 0; c < M; ++c) p.u[c] += zc0 * p.s1;
+      p.tbase = zc0 * p.ts1;
       p.no1 = zcn;
       nother = zcn * nbatch;
       if (scatter) p.dst_base += zc0 * p.dst_s1;
-      if (scatter && slab_yocc1) p.occ1 = 1;
+      if (scatter && slab_yocc1 && !to_stage) p.occ1 = 1;
     }
     int rc = prof_begin(mode == 1 ? KC_STR_D : KC_STR_FI);
     if (rc) return rc;
@@ -1352,11 +1387,79 @@ struct PlanT : PlanBase {
   // [forward y pass of step s, its results stored straight into the peers' y-slabs over NVLink] -- touches every
   // z-plane independently, so it runs in `slab_chunks` chunks of planes alternating between two streams: while one
   // chunk's forward pass is bound by its NVLink stores, the next chunk's local kernels (HBM-bound) run beside it.
+  int ce_setup() {
+    if (ce_stream[0]) return 0;
+    int rc;
+    const size_t bytes = sizeof(cpx<T>) * (size_t)nspatial;
+    for (int c = 0; c < M; ++c)
+      if ((rc = dalloc((void**)&stage[c], bytes))) return rc;
+    for (int i = 0; i < 2; ++i) {
+      GGP_CUDA(cudaStreamCreateWithFlags(&ce_stream[i], cudaStreamNonBlocking));
+      GGP_CUDA(cudaEventCreateWithFlags(&ev_ce[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 16; ++i) GGP_CUDA(cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming));
+    return 0;
+  }
+  // the plan's stream waits for every copy issued so far on the copy-engine streams
+  int ce_join() {
+    for (int i = 0; i < 2; ++i) {
+      GGP_CUDA(cudaEventRecord(ev_ce[i], ce_stream[i]));
+      GGP_CUDA(cudaStreamWaitEvent(stream, ev_ce[i], 0));
+    }
+    return 0;
+  }
+  // copies of one chunk of the forward transpose: z-planes [z0, z1) of every remote block, contiguous on both sides
+  int ce_push_y(int chunk, cudaStream_t produced_on, long long z0, long long z1) {
+    cudaStream_t cs = ce_stream[chunk & 1];
+    GGP_CUDA(cudaEventRecord(ev_chunk[chunk & 15], produced_on));
+    GGP_CUDA(cudaStreamWaitEvent(cs, ev_chunk[chunk & 15], 0));
+    const long long blk = n[0] * n2loc * n3loc, plane = n[0] * n2loc;
+    const long long dbase = plane * (long long)prank * n3loc;
+    for (int i = 1; i < P; ++i) {
+      const int q = (prank + i) % P;          // every rank starts with a different peer
+      for (int c = 0; c < M; ++c)
+        GGP_CUDA(cudaMemcpyAsync(peer_x[q][c] + dbase + z0 * plane, stage[c] + (long long)q * blk + z0 * plane,
+                                 sizeof(cpx<T>) * (size_t)((z1 - z0) * plane), cudaMemcpyDefault, cs));
+    }
+    return 0;
+  }
+  // copies of one chunk of the backward transpose: rows [y0, y1) of every block, n3loc pieces of n1 * (y1 - y0)
+  int ce_push_z(int chunk, cudaStream_t produced_on, long long y0, long long y1) {
+    cudaStream_t cs = ce_stream[chunk & 1];
+    GGP_CUDA(cudaEventRecord(ev_chunk[chunk & 15], produced_on));
+    GGP_CUDA(cudaStreamWaitEvent(cs, ev_chunk[chunk & 15], 0));
+    const long long blk = n[0] * n2loc * n3loc;
+    const size_t esz = sizeof(cpx<T>);
+    for (int i = 0; i < P; ++i) {
+      const int q = (prank + i) % P;
+      for (int c = 0; c < M; ++c)
+        GGP_CUDA(cudaMemcpy2DAsync(peer_u[q][c] + n[0] * ((long long)prank * n2loc + y0), esz * (size_t)(n[0] * n2g),
+                                   stage[c] + (long long)q * blk + n[0] * y0, esz * (size_t)(n[0] * n2loc),
+                                   esz * (size_t)(n[0] * (y1 - y0)), (size_t)n3loc, cudaMemcpyDefault, cs));
+    }
+    return 0;
+  }
+  // z pass of the y-slab (forward FFT_z x exp_D x inverse FFT_z) with its results sent back to the z-slabs
+  int slab_z() {
+    int rc;
+    if (!slab_ce) return run_str(2, 1, true, 2);
+    int C = (profiling || flush_buf) ? 1 : slab_chunks;
+    if (C > n2loc) C = (int)n2loc;
+    if (C < 1) C = 1;
+    for (int c = 0; c < C; ++c) {
+      const long long y0 = (long long)c * n2loc / C, y1 = (long long)(c + 1) * n2loc / C;
+      if ((rc = run_str(2, 1, true, 2, y0, y1 - y0, stream, true))) return rc;
+      if ((rc = ce_push_z(c, stream, y0, y1))) return rc;
+    }
+    return ce_join();
+  }
+
   int slab_iry(bool do_inv, bool pre, bool post, const HalfStep<T>& hA, const HalfStep<T>& hB, bool do_y) {
     int rc;
     int C = (profiling || flush_buf) ? 1 : slab_chunks;
     if (C > n3loc) C = (int)n3loc;
     if (C < 1) C = 1;
+    if (slab_ce && (rc = ce_setup())) return rc;
     if (C > 1) {
       if (!aux_stream) {
         GGP_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
@@ -1371,12 +1474,14 @@ struct PlanT : PlanBase {
       const long long z0 = (long long)c * n3loc / C, z1 = (long long)(c + 1) * n3loc / C;
       if (do_inv && (rc = run_str(1, 2, false, 0, z0, z1 - z0, st))) return rc;
       if ((rc = run_row(pre, post, hA, hB, z0, z1 - z0, st))) return rc;
-      if (do_y && (rc = run_str(1, 0, false, 1, z0, z1 - z0, st))) return rc;
+      if (do_y && (rc = run_str(1, 0, false, 1, z0, z1 - z0, st, slab_ce))) return rc;
+      if (do_y && slab_ce && (rc = ce_push_y(c, st, z0, z1))) return rc;
     }
     if (C > 1) {
       GGP_CUDA(cudaEventRecord(ev_join, aux_stream));
       GGP_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     }
+    if (do_y && slab_ce) return ce_join();
     return 0;
   }
 
@@ -1501,6 +1606,7 @@ struct PlanT : PlanBase {
     p2p = getenv("GGP_SLAB_NCCL") == nullptr;
     if (const char* e = getenv("GGP_SLAB_CHUNKS")) slab_chunks = atoi(e) > 0 ? atoi(e) : 1;
     slab_yocc1 = getenv("GGP_SLAB_YOCC1") != nullptr;
+    slab_ce = getenv("GGP_SLAB_CE") != nullptr && atoi(getenv("GGP_SLAB_CE")) != 0;
     return 0;
   }
   int barrier_status() {
@@ -1623,7 +1729,7 @@ struct PlanT : PlanBase {
         if ((rc = next_half(s, 1, 1, &prev2))) return rc;
         if ((rc = window_begin())) return rc;
         if ((rc = slab_barrier())) return rc;
-        if ((rc = run_str(2, 1, true, 2))) return rc;
+        if ((rc = slab_z())) return rc;
         if ((rc = slab_barrier())) return rc;
         continue;
       }

@@ -62,6 +62,7 @@ struct alignas(64) StrParams {
   long long ntx;     // tiles of W along the fast axis
   long long no1, s1, s2;  // remaining dims: offset = (o % no1) * s1 + (o / no1) * s2
   long long ts1;     // table stride of remaining dim 1 (tables do not have the batch dim)
+  long long tbase;   // table offset of the first group of a chunked launch (0 otherwise)
   const cpx<T>* D[4];
   const typename TwT<T>::type* Dsp[2];  // KIND_SEP factors (D_perp, D_line) as hi + lo pairs (fp32 plans)
   int dkind;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(KCfg<T, N>::str_max_threads(M), KCfg<T, N>::st
   const long long xt = g % p.ntx, o = g / p.ntx;
   const long long o1 = o % p.no1, o2 = o / p.no1;
   const long long off = xt * W + xw + o1 * p.s1 + o2 * p.s2 + (long long)t * p.ls;
-  const long long toff = xt * W + xw + o1 * p.ts1 + (long long)t * p.ls;
+  const long long toff = xt * W + xw + o1 * p.ts1 + p.tbase + (long long)t * p.ls;
   const long long mstride = (long long)TPL * p.ls;
   cpx<T>* sl = smem + (size_t)xw * M * LS;
 

@@ -1,6 +1,7 @@
 """3-D slab decomposition (BASELINE config C5's shape): z-slabs on 2, 4 and 8 GPUs, compared with the unsharded
-CPU oracle -- once with the transposes fused into the FFT kernels as peer stores over NVLink (CUDA IPC, the
-default), once with the ncclSend/ncclRecv transposes.  Every world size exercises its own scatter index math
+CPU oracle -- with the transposes fused into the FFT kernels as peer stores over NVLink (CUDA IPC), with the scatter
+passes writing a local staging buffer that the copy engines push to the peers (GGP_SLAB_CE=1), and with the
+ncclSend/ncclRecv transposes.  Every world size exercises its own scatter index math
 (`dst_shift`, `dst_base` of StrParams).  Needs >= `world` CUDA devices (gpurun --gpus N); smaller boxes skip."""
 import os
 import sys
@@ -45,7 +46,10 @@ def _cases(ns):
     return out
 
 
-def _worker(rank, world, port, q, p2p):
+def _worker(rank, world, port, q, mode):
+    p2p = mode != "nccl"
+    if mode == "copy_engines":          # scatter passes write a local staging buffer, the copy engines push it
+        os.environ["GGP_SLAB_CE"] = "1"
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -76,8 +80,9 @@ def _worker(rank, world, port, q, p2p):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("p2p", [True, False], ids=["peer_stores", "nccl"])
-def test_slab_decomposition_matches_oracle(p2p, world):
+@pytest.mark.parametrize("mode", ["peer_stores", "nccl", "copy_engines"])
+def test_slab_decomposition_matches_oracle(mode, world):
+    p2p = mode != "nccl"
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -85,8 +90,8 @@ def test_slab_decomposition_matches_oracle(p2p, world):
     import ggp_oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300) + (301 if p2p else 0) + 7 * world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, p2p)) for r in range(world)]
+    port = 29600 + (os.getpid() % 300) + {"peer_stores": 301, "nccl": 0, "copy_engines": 602}[mode] + 7 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     results = q.get(timeout=600)

@@ -3,7 +3,7 @@
 # pipeline at N = 8, and the full default bench line at N = 8.   TAG=r02g bash tools/evidence_8gpu.sh
 TAG=${TAG:-r02g}
 mkdir -p gpurun_out
-(time timeout 900 python -m pytest tests/test_gpu_slab.py -q -x -k "peer_stores and (4 or 8)") > gpurun_out/pytest_slab_${TAG}.log 2>&1
+(time timeout 900 python -m pytest tests/test_gpu_slab.py -q -x -k "(peer_stores or copy_engines) and (4 or 8)") > gpurun_out/pytest_slab_${TAG}.log 2>&1
 tail -4 gpurun_out/pytest_slab_${TAG}.log
 run() {  # name grid env...
   name=$1; grid=$2; shift 2
