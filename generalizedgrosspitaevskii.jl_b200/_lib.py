@@ -9,10 +9,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggp.so")
 LIB_PATH = os.environ.get("GGP_LIBRARY", LIB_PATH)  # A/B measurements of kernel variants (tools/)
 
-GGP_ABI_VERSION = 4
+GGP_ABI_VERSION = 5
+GGP_MAX_COMPONENTS = 4
 GGP_C64, GGP_C128 = 0, 1
 TABLE_NONE, TABLE_SCALAR, TABLE_DIAG, TABLE_FULL, TABLE_SEP_AXES = 0, 1, 2, 3, 4
-NL_NONE, NL_DIAG = 0, 1
+NL_NONE, NL_DIAG, NL_MATRIX = 0, 1, 2
 PUMP_NONE, PUMP_SEPARABLE, PUMP_DENSE = 0, 1, 2
 NOISE_NONE, NOISE_CONST, NOISE_FIELD = 0, 1, 2
 OBS_DENSITY, OBS_MOMENTUM, OBS_NORM, OBS_G2_MOMENTUM = 0, 1, 2, 3
@@ -51,6 +52,8 @@ class GgpDesc(C.Structure):
         ("disp_sep_tol", C.c_double),
         ("disp_axes", C.c_void_p * 3),
         ("mixed_precision_tables", C.c_int32), ("reserved1", C.c_int32),
+        ("nl_c_ext", C.c_void_p), ("nl_g_ext", C.c_void_p),
+        ("noise_eta_ext", C.c_void_p), ("noise_alpha_ext", C.c_void_p),
     ]
 
 

@@ -405,6 +405,10 @@ struct PlanBase {
   }
 };
 
+}  // namespace ggp
+#include "generic_plan.cuh"
+namespace ggp {
+
 template <typename T>
 struct PlanT : PlanBase {
   int ndim = 0, M = 0;
@@ -1942,7 +1946,12 @@ int ggp_plan_create(const ggp_desc* d, ggp_plan** out) {
   if (d->slab_nranks < 0 || d->slab_nranks == 1) { /* 0 or 1: no slab decomposition */ }
   if (d->struct_size != sizeof(ggp_desc)) return fail(GGP_ERR_INVALID, "struct_size mismatch");
   if (d->ndim < 1 || d->ndim > 3) return fail(GGP_ERR_INVALID, "ndim must be 1..3");
-  if (d->ncomp < 1 || d->ncomp > 2) return fail(GGP_ERR_UNSUPPORTED, "ncomp must be 1 or 2");
+  if (d->ncomp < 1 || d->ncomp > GGP_MAX_COMPONENTS)
+    return fail(GGP_ERR_UNSUPPORTED, "ncomp must be 1.." + std::to_string(GGP_MAX_COMPONENTS));
+  for (int i = 0; i < d->ndim; ++i)
+    if (!gen_axis_supported(d->n[i]))
+      return fail(GGP_ERR_UNSUPPORTED, "axis length " + std::to_string(d->n[i]) +
+                                           " is beyond the built transform sizes (powers of two up to 8192, any n up to 4096)");
   if (d->nbatch < 1) return fail(GGP_ERR_INVALID, "nbatch must be >= 1");
   for (int i = 0; i < d->ndim; ++i)
     if (d->n[i] < 1) return fail(GGP_ERR_INVALID, "n[i] must be >= 1");
@@ -1960,7 +1969,11 @@ int ggp_plan_create(const ggp_desc* d, ggp_plan** out) {
   }
   if (dev >= ndev) return fail(GGP_ERR_INVALID, "device ordinal out of range");
   GGP_CUDA(cudaSetDevice(dev));
-  PlanBase* impl = d->precision == GGP_C64 ? (PlanBase*)new PlanT<float>() : (PlanBase*)new PlanT<double>();
+  PlanBase* impl;
+  if (gen_wanted(*d))   // any axis length, ncomp > 2, matrix-valued nonlinearity (generic_plan.cuh)
+    impl = d->precision == GGP_C64 ? (PlanBase*)new GenPlanT<float>() : (PlanBase*)new GenPlanT<double>();
+  else
+    impl = d->precision == GGP_C64 ? (PlanBase*)new PlanT<float>() : (PlanBase*)new PlanT<double>();
   impl->device = dev;
   int rc = impl->create(*d);
   if (rc) {

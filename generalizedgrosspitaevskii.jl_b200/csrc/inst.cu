@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 #include "kernels.cuh"
+#include "generic.cuh"
 #ifdef GGP_TMA
 #include "str_tma.cuh"
 #endif
@@ -337,6 +338,22 @@ int launch_str2(StrParams<float> p, long long nfast, long long nother, cudaStrea
 template int launch_row2<GGP_N>(const RowParams<float>&, cudaStream_t);
 template int launch_str2<GGP_N>(StrParams<float>, long long, long long, cudaStream_t);
 #endif
+
+// generic (unfused) line transform of the generic plan: plain for n == L, Bluestein for n < L (generic.cuh)
+template <typename T, int L>
+int launch_gen_fft(GenFftParams<T> p, cudaStream_t st) {
+  int threads = 0;
+  size_t smem = 0;
+  gen_fft_geometry<T, L>(p.sa, &p.W, &p.LS, &threads, &smem);
+  const long long grid = (p.nlines + p.W - 1) / p.W;
+  if (grid > 0x7fffffffLL || grid < 1) return (int)cudaErrorInvalidConfiguration;
+  auto k = gen_fft_kernel<T, L>;
+  int e = set_smem(k, smem);
+  if (e) return e;
+  k<<<(unsigned)grid, threads, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+template int launch_gen_fft<GGP_T, GGP_N>(GenFftParams<GGP_T>, cudaStream_t);
 
 template int launch_row<GGP_T, GGP_N>(int, int, const RowParams<GGP_T>&, cudaStream_t);
 template int launch_str<GGP_T, GGP_N>(int, StrParams<GGP_T>, long long, long long, cudaStream_t);

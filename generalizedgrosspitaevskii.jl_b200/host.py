@@ -246,6 +246,18 @@ def _expm2(a, c, b, d):
     return (g * (a - d) + f + e) / 2 + 1, g * c, g * b, (-g * (a - d) + f + e) / 2 + 1  # m11 m21 m12 m22
 
 
+def _expm_batched(A):
+    """exp of a stack of small matrices (..., M, M), M > 2: scaling and squaring with a Pade approximant
+    (scipy.linalg.expm, the algorithm family StaticArrays / LinearAlgebra use for sizes beyond 2x2)."""
+    import scipy.linalg
+    A = np.asarray(A, dtype=complex)
+    flat = A.reshape((-1,) + A.shape[-2:])
+    # identical points (constant couplings on a large grid) are exponentiated once
+    uniq, inv = np.unique(flat.reshape(flat.shape[0], -1), axis=0, return_inverse=True)
+    out = np.stack([scipy.linalg.expm(m.reshape(A.shape[-2:])) for m in uniq])
+    return out[np.asarray(inv).reshape(-1)].reshape(A.shape)
+
+
 def exp_table(f, grid, param, dt, M):
     """Returns (kind, AoS array of shape (npoints, ncols) complex) for cis(-dt * f(point, param))."""
     if _absent(f):
@@ -262,10 +274,15 @@ def exp_table(f, grid, param, dt, M):
         cols = [np.broadcast_to(_cis(-dt * np.asarray(v)), shape) for v in val]
         kind = L.TABLE_DIAG
     elif isinstance(val, SMatrix):
-        if val.n != M or M != 2:
-            raise UnsupportedForm("matrix-valued tables are supported for 2x2 (M = 2) only")
-        m11, m21, m12, m22 = _expm2(*(1j * (-dt * np.asarray(val[i, j])) for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))))
-        cols = [np.broadcast_to(m, shape) for m in (m11, m21, m12, m22)]  # column-major like SMatrix
+        if val.n != M:
+            raise ValueError("SMatrix table must be M x M")
+        if M == 2:
+            m11, m21, m12, m22 = _expm2(*(1j * (-dt * np.asarray(val[i, j])) for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))))
+            cols = [np.broadcast_to(m, shape) for m in (m11, m21, m12, m22)]  # column-major like SMatrix
+        else:
+            E = _expm_batched(np.stack([np.stack([np.broadcast_to(1j * (-dt * np.asarray(val[i, j], dtype=complex)), shape)
+                                                  for j in range(M)], axis=-1) for i in range(M)], axis=-2))
+            cols = [E[..., i, j] for j in range(M) for i in range(M)]          # column-major: (1,1) (2,1) ... (M,M)
         kind = L.TABLE_FULL
     else:
         cols = [np.broadcast_to(_cis(-dt * np.asarray(val)), shape)]
@@ -363,8 +380,11 @@ def dispersion_axis_factors(f, grid, param, dt):
 
 
 def recognise_nonlinearity(f, param, M, rng=None):
-    """Fit G_i(u) = c_i + sum_j g_ij |u_j|^2 by probing the closure; verify on held-out samples.
-    Returns (scalar_flag, c[M] complex, g[M][M] complex)."""
+    """Fit the closure by probing and verify on held-out samples.  Registered forms:
+      Number / SVector   G_i(u)  = c_i  + sum_j g_ij  |u_j|^2    -> ("scalar" | "vector", c[M], g[M][M])
+      SMatrix (M x M)    G_ij(u) = C_ij + sum_k g_ijk |u_k|^2    -> ("matrix", C[M][M], g[M][M][M])
+    (the matrix form: src/kernels.jl:22-25 -- `cis` of an SMatrix is the matrix exponential, docs
+    general_overview.md:77)."""
     rng = rng or np.random.default_rng(0xC0FFEE)
     P = 4 * (M + 1) + 8
 
@@ -375,24 +395,29 @@ def recognise_nonlinearity(f, param, M, rng=None):
 
     def evaluate(u):
         val = f(SVector([u[j] for j in range(M)]), param)
-        scalar = True
+        kind = "scalar"
         if isinstance(val, SMatrix):
-            if val.n != 1:
-                raise UnsupportedForm("matrix-valued nonlinearity (docs general_overview.md:77) is not a registered form")
-            val = SVector(val[0, 0])
+            if val.n == 1:
+                val = SVector(val[0, 0])
+            elif val.n == M:
+                rows = [np.broadcast_to(np.asarray(val[i, j], dtype=complex), u.shape[1:])
+                        for i in range(M) for j in range(M)]
+                return "matrix", np.stack(rows)
+            else:
+                raise UnsupportedForm("matrix-valued nonlinearity must be M x M")
         if isinstance(val, SVector):
-            scalar = False
+            kind = "vector"
             if len(val) == 1 and isinstance(val[0], SVector):
                 val = val[0]
             rows = [np.broadcast_to(np.asarray(v, dtype=complex), u.shape[1:]) for v in val]
         else:
             rows = [np.broadcast_to(np.asarray(val, dtype=complex), u.shape[1:])]
-        return scalar, np.stack(rows)
+        return kind, np.stack(rows)
 
     u = probe(P)
-    scalar, G = evaluate(u)
-    if not scalar and G.shape[0] != M:
-        raise UnsupportedForm("nonlinearity must return a Number or an SVector of length M")
+    kind, G = evaluate(u)
+    if kind == "vector" and G.shape[0] != M:
+        raise UnsupportedForm("nonlinearity must return a Number, an SVector of length M or an M x M SMatrix")
     A = np.concatenate([np.ones((1, P)), np.abs(u) ** 2], axis=0).T        # (P, M+1)
     coef, *_ = np.linalg.lstsq(A, G.T, rcond=None)                          # (M+1, rows)
     v = probe(16)
@@ -400,8 +425,14 @@ def recognise_nonlinearity(f, param, M, rng=None):
     pred = (np.concatenate([np.ones((1, 16)), np.abs(v) ** 2], axis=0).T @ coef).T
     scale = max(1e-300, np.abs(Gv).max(), np.abs(coef).max())
     if np.abs(pred - Gv).max() > 1e-9 * scale:
-        raise UnsupportedForm("nonlinearity is not of the registered form c_i + sum_j g_ij |u_j|^2 "
-                              "(the B200 backend has no CPU fallback)")
+        raise UnsupportedForm("nonlinearity is not of a registered form (c_i + sum_j g_ij |u_j|^2, or the same per "
+                              "entry of an SMatrix); the B200 backend has no CPU fallback")
+    coef = coef.copy()
+    coef[np.abs(coef) < 1e-13 * scale] = 0                                  # round-off of the fit
+    if kind == "matrix":
+        Cm = coef[0].reshape(M, M)
+        g = coef[1:].T.reshape(M, M, M)                                     # g[i][j][k]
+        return "matrix", Cm, g
     rows = G.shape[0]
     c = np.zeros(M, dtype=complex)
     g = np.zeros((M, M), dtype=complex)
@@ -409,10 +440,9 @@ def recognise_nonlinearity(f, param, M, rng=None):
         src = 0 if rows == 1 else i
         c[i] = coef[0, src]
         g[i, :] = coef[1:, src]
-    # clean round-off of the fit
-    c[np.abs(c) < 1e-13 * scale] = 0
-    g[np.abs(g) < 1e-13 * scale] = 0
-    return scalar or rows == 1 and M == 1, c, g
+    if kind == "vector" and rows == 1 and M == 1:
+        kind = "scalar"
+    return kind, c, g
 
 
 class PumpModel:
@@ -695,6 +725,7 @@ class StrangSplittingIterator:
         daxes = None
         npts_full = int(np.prod(sizes))
         if (M == 1 and prob.ndim >= 2 and not _absent(prob.dispersion)
+                and all(int(n_) & (int(n_) - 1) == 0 for n_ in sizes)
                 and npts_full >= int(os.environ.get("GGP_SEP_AXES_MIN", 1 << 26))):
             rg_full = reciprocal_grid(prob_g) if slab is not None else rg
             daxes = dispersion_axis_factors(prob.dispersion, rg_full, prob.param, self.dt)
@@ -738,13 +769,22 @@ class StrangSplittingIterator:
         d.pot_table = as_c128(vtab) if vtab is not None else None
 
         if not _absent(prob.nonlinearity):
-            scalar, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, M)
-            d.nl_kind, d.nl_scalar = L.NL_DIAG, int(bool(scalar))
-            for i in range(M):
-                d.nl_c[i][0], d.nl_c[i][1] = c[i].real, c[i].imag
-                for j in range(M):
-                    d.nl_g[i][j][0], d.nl_g[i][j][1] = g[i, j].real, g[i, j].imag
-            self.nl = (scalar, c, g)
+            kind, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, M)
+            scalar = kind == "scalar"
+            if kind == "matrix" or M > 2:
+                # generic plan (ABI 5): coefficient arrays of any M
+                d.nl_kind, d.nl_scalar = (L.NL_MATRIX if kind == "matrix" else L.NL_DIAG), int(scalar)
+                cc = c if kind != "scalar" else c[:1]
+                gg = g if kind != "scalar" else g[:1]
+                d.nl_c_ext = as_c128(np.asarray(cc, dtype=np.complex128).reshape(-1))
+                d.nl_g_ext = as_c128(np.asarray(gg, dtype=np.complex128).reshape(-1))
+            else:
+                d.nl_kind, d.nl_scalar = L.NL_DIAG, int(scalar)
+                for i in range(M):
+                    d.nl_c[i][0], d.nl_c[i][1] = c[i].real, c[i].imag
+                    for j in range(M):
+                        d.nl_g[i][j][0], d.nl_g[i][j][1] = g[i, j].real, g[i, j].imag
+            self.nl = (kind, c, g)
 
         # pump amplitude schedule at the reference's times
         nsteps = nsaves * self.steps_per_save
@@ -800,10 +840,14 @@ class StrangSplittingIterator:
             if field and slab is not None:
                 raise UnsupportedForm("field-/position-dependent noise with a slab decomposition")
             d.noise_kind, d.noise_real = (L.NOISE_FIELD if field else L.NOISE_CONST), int(self.noise_real)
-            for i in range(M):
-                d.noise_eta[i][0], d.noise_eta[i][1] = eta[i].real, eta[i].imag
-                for j in range(M):
-                    d.noise_alpha[i][j][0], d.noise_alpha[i][j][1] = alpha[i, j].real, alpha[i, j].imag
+            if M > 2:
+                d.noise_eta_ext = as_c128(np.asarray(eta, dtype=np.complex128).reshape(-1))
+                d.noise_alpha_ext = as_c128(np.asarray(alpha, dtype=np.complex128).reshape(-1))
+            else:
+                for i in range(M):
+                    d.noise_eta[i][0], d.noise_eta[i][1] = eta[i].real, eta[i].imag
+                    for j in range(M):
+                        d.noise_alpha[i][j][0], d.noise_alpha[i][j][1] = alpha[i, j].real, alpha[i, j].imag
             if profile is not None:
                 d.noise_profile = as_c128(profile)
             self.noise_form = (eta, alpha, profile)

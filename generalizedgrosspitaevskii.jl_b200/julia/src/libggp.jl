@@ -6,7 +6,8 @@
 # mirror (../host.py) implements the same logic line for line and IS exercised by the test-suite.
 using Libdl
 
-const GGP_ABI_VERSION = UInt32(4)
+const GGP_ABI_VERSION = UInt32(5)
+const GGP_MAX_COMPONENTS = 4
 const GGP_C64, GGP_C128 = Int32(0), Int32(1)
 const GGP_TABLE_NONE, GGP_TABLE_SCALAR, GGP_TABLE_DIAG, GGP_TABLE_FULL, GGP_TABLE_SEP_AXES = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
 const GGP_PUMP_NONE, GGP_PUMP_SEPARABLE, GGP_PUMP_DENSE = Int32(0), Int32(1), Int32(2)
@@ -51,6 +52,11 @@ struct GgpDesc
     disp_axes::NTuple{3,Ptr{Cvoid}}  # GGP_TABLE_SEP_AXES (ABI 4): per-axis factors of a scalar exp_D, else C_NULL
     mixed_precision_tables::Int32    # 1: ComplexF32 fields with ComplexF64 tables in the reference (quirk Q6)
     reserved1::Int32
+    # ABI 5 (generic plan: M > 2, SMatrix nonlinearities): flat (re, im) coefficient arrays, C_NULL when unused
+    nl_c_ext::Ptr{Cvoid}             # c_i (M) / C_ij (M², [i][j] row-major)
+    nl_g_ext::Ptr{Cvoid}             # g_ij (M², [i][j]) / g_ijk (M³, [i][j][k])
+    noise_eta_ext::Ptr{Cvoid}        # η_i (M)
+    noise_alpha_ext::Ptr{Cvoid}      # α_ij (M², [i][j])
 end
 
 const _lib = Ref{Ptr{Cvoid}}(C_NULL)

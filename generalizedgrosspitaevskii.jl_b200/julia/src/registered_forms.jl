@@ -2,36 +2,56 @@
 # device are matched against the registered forms by probing (SURVEY §7 hard part 2, §8a).
 # An unrecognised closure throws -- the B200 backend has no CPU fallback.
 
-_aslist(x::Number, M) = (ntuple(_ -> ComplexF64(x), M), true)
-_aslist(x::SVector, M) = (ntuple(i -> ComplexF64(x[i]), M), false)
-_aslist(x::SMatrix{1,1}, M) = (ntuple(_ -> ComplexF64(x[1]), M), false)
+_aslist(x::Number, M) = (ntuple(_ -> ComplexF64(x), M), :scalar)
+_aslist(x::SVector, M) = (ntuple(i -> ComplexF64(x[i]), M), :vector)
+_aslist(x::SMatrix{1,1}, M) = (ntuple(_ -> ComplexF64(x[1]), M), :vector)
+# M x M SMatrix (M > 1): the M² entries row-major [i][j]  (src/kernels.jl:22-25: cis(::SMatrix) is the matrix exponential)
+_aslist(x::SMatrix{K,K}, M) where {K} = (ntuple(k -> ComplexF64(x[(k-1)÷K+1, (k-1)%K+1]), K * K), :matrix)
 
-"G_i(u) = c_i + Σ_j g_ij |u_j|²  ->  (scalar::Bool, c::Vector{ComplexF64}, g::Matrix{ComplexF64})"
+"""
+Registered nonlinearity forms (host.py: recognise_nonlinearity), fitted by probing and verified on held-out samples:
+  Number / SVector   G_i(u)  = c_i  + Σ_j g_ij |u_j|²    -> (:scalar | :vector, c::Vector (M), g::Matrix (M × M))
+  SMatrix (M × M)    G_ij(u) = C_ij + Σ_k g_ijk |u_k|²   -> (:matrix, C::Matrix (M × M), g::Array (M × M × M))
+"""
 function recognise_nonlinearity(f, param, ::Val{M}) where {M}
     rng = Random.Xoshiro(0xC0FFEE)
     P = 4 * (M + 1) + 8
     probe() = SVector{M,ComplexF64}(ntuple(_ -> (0.2 + 1.8 * rand(rng)) * cis(2π * rand(rng)), M))
     us = [probe() for _ in 1:P]
     vals = [_aslist(f(u, param), M) for u in us]
-    scalar = vals[1][2]
+    kind = vals[1][2]
+    nrows = length(vals[1][1])                       # M, or M² for the matrix form
     A = [j == 0 ? 1.0 : abs2(us[p][j]) for p in 1:P, j in 0:M]
-    c = zeros(ComplexF64, M); g = zeros(ComplexF64, M, M)
-    for i in 1:M
+    c = zeros(ComplexF64, nrows); g = zeros(ComplexF64, nrows, M)
+    for i in 1:nrows
         coef = A \ ComplexF64[v[1][i] for v in vals]
         c[i] = coef[1]; g[i, :] .= coef[2:end]
     end
     scale = max(maximum(abs, c), maximum(abs, g), floatmin(Float64))
     for _ in 1:16                                    # held-out verification (also catches phase dependence)
         u = probe(); v = _aslist(f(u, param), M)[1]
-        for i in 1:M
+        for i in 1:nrows
             pred = c[i] + sum(g[i, j] * abs2(u[j]) for j in 1:M)
             abs(pred - v[i]) ≤ 1e-9 * max(scale, abs(v[i])) ||
-                error("nonlinearity is not of the registered form c_i + Σ_j g_ij |u_j|² (no CPU fallback)")
+                error("nonlinearity is not of a registered form (c_i + Σ_j g_ij |u_j|², or the same per entry of an SMatrix); no CPU fallback")
         end
     end
     c[abs.(c).<1e-13*scale] .= 0; g[abs.(g).<1e-13*scale] .= 0
-    scalar, c, g
+    if kind == :matrix
+        # rows are [i][j] row-major: C[i,j] = c[(i-1)M+j], G3[i,j,k] = g[(i-1)M+j, k]
+        C = [c[(i-1)*M+j] for i in 1:M, j in 1:M]
+        G3 = [g[(i-1)*M+j, k] for i in 1:M, j in 1:M, k in 1:M]
+        return :matrix, C, G3
+    end
+    kind, c, g
 end
+
+# flat (re, im) Float64 arrays in the row-major [i][j]([k]) order of include/ggp.h (Julia arrays are column-major)
+_reim_rowmajor(v::AbstractVector) = Float64[f(x) for x in v for f in (real, imag)]
+_reim_rowmajor(m::AbstractMatrix) = Float64[f(m[i, j]) for i in axes(m, 1) for j in axes(m, 2) for f in (real, imag)]
+_reim_rowmajor(a::AbstractArray{<:Any,3}) =
+    Float64[f(a[i, j, k]) for i in axes(a, 1) for j in axes(a, 2) for k in axes(a, 3) for f in (real, imag)]
+_fptr(v::Vector{Float64}) = isempty(v) ? Ptr{Cvoid}(C_NULL) : Ptr{Cvoid}(pointer(v))
 
 "The pump closure on the whole direct grid at time t, point-major then component (grid_map!, src/misc.jl:34-37)"
 function pump_on_grid(pump, prob, t)

@@ -62,15 +62,25 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
     sep_tol = (CT == ComplexF32 && dkind == GGP_TABLE_SCALAR && exp_D isa AbstractArray{<:Number}) ?
               separable_dispersion_tol(prob.dispersion, rg, prob.param, exp_D) : 0.0
 
+    M ≤ GGP_MAX_COMPONENTS || error("the B200 backend is built for up to $GGP_MAX_COMPONENTS components")
     nl_kind = Int32(0); nl_scalar = Int32(0); nl_c = ntuple(_ -> 0.0, 4); nl_g = ntuple(_ -> 0.0, 8)
+    nl_c_ext = Float64[]; nl_g_ext = Float64[]          # ABI 5: M > 2 and SMatrix nonlinearities (generic plan)
     if !(prob.nonlinearity isa AdditiveIdentity)
-        sc, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, Val(M))
-        nl_kind = Int32(1); nl_scalar = Int32(sc)
-        nl_c = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(c[i]) : imag(c[i]))), 4)
-        nl_g = ntuple(k -> begin
-                i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
-                (i > M || j > M) ? 0.0 : (isodd(k) ? real(g[i, j]) : imag(g[i, j]))
-            end, 8)
+        kind, c, g = recognise_nonlinearity(prob.nonlinearity, prob.param, Val(M))
+        nl_scalar = Int32(kind == :scalar)
+        if kind == :matrix || M > 2
+            nl_kind = Int32(kind == :matrix ? 2 : 1)
+            # a Number-valued closure: one row (c, g_j); SVector: M rows; SMatrix: C_ij and g_ijk
+            nl_c_ext = _reim_rowmajor(kind == :scalar ? c[1:1] : c)
+            nl_g_ext = _reim_rowmajor(kind == :scalar ? g[1:1, :] : g)
+        else
+            nl_kind = Int32(1)
+            nl_c = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(c[i]) : imag(c[i]))), 4)
+            nl_g = ntuple(k -> begin
+                    i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
+                    (i > M || j > M) ? 0.0 : (isodd(k) ? real(g[i, j]) : imag(g[i, j]))
+                end, 8)
+        end
     end
 
     # pump amplitudes at the reference's times: t is incremented BEFORE step! (SURVEY Q1)
@@ -101,6 +111,7 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
 
     noise_kind = Int32(0); noise_real = Int32(0); eta = ntuple(_ -> 0.0, 4); seed = UInt64(0)
     alpha = ntuple(_ -> 0.0, 8); nprof = ComplexF64[]
+    eta_ext = Float64[]; alpha_ext = Float64[]          # ABI 5: M > 2
     if !(prob.position_noise_func isa AdditiveIdentity)
         e, al, P = recognise_noise(prob.position_noise_func, prob)
         # the reference indexes ξ with the leading ndims(ξ) indices only (src/kernels.jl:24,27): a prototype without
@@ -111,12 +122,16 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
             error("noise_prototype arrays must be all real or all complex")
         field = any(!iszero, al) || P !== nothing
         noise_kind = Int32(field ? 2 : 1); noise_real = Int32(eltype(first(prob.noise_prototype)) <: Real)
-        alpha = ntuple(k -> begin
-                i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
-                (i > M || j > M) ? 0.0 : (isodd(k) ? real(al[i, j]) : imag(al[i, j]))
-            end, 8)
         P === nothing || (nprof = P)
-        eta = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(e[i]) : imag(e[i]))), 4)
+        if M > 2
+            eta_ext = _reim_rowmajor(collect(e)); alpha_ext = _reim_rowmajor(al)
+        else
+            alpha = ntuple(k -> begin
+                    i = (k - 1) ÷ 4 + 1; j = ((k - 1) ÷ 2) % 2 + 1
+                    (i > M || j > M) ? 0.0 : (isodd(k) ? real(al[i, j]) : imag(al[i, j]))
+                end, 8)
+            eta = ntuple(k -> (i = (k - 1) ÷ 2 + 1; i > M ? 0.0 : (isodd(k) ? real(e[i]) : imag(e[i]))), 4)
+        end
         seed = rng === nothing ? rand(UInt64) : rand(rng, UInt64)
     end
 
@@ -126,8 +141,9 @@ function init(prob::GrossPitaevskiiProblem{N,M}, ::StrangSplitting, tspan;
         dkind, vkind, _ptr(dflat), _ptr(vflat), nl_kind, nl_scalar, nl_c, nl_g,
         pump_kind, pump_ncomp, _ptr(sflat), amp0, noise_kind, noise_real, eta, seed, Int32(0), Int32(0),
         alpha, _ptr(nprof), sep_tol, (Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL), Ptr{Cvoid}(C_NULL)),
-        Int32(CT == ComplexF32 && exp_D isa AbstractArray && real(eltype(eltype(exp_D))) == Float64), Int32(0))
-    handle = GC.@preserve dflat vflat sflat nprof ggp_plan_create(desc)
+        Int32(CT == ComplexF32 && exp_D isa AbstractArray && real(eltype(eltype(exp_D))) == Float64), Int32(0),
+        _fptr(nl_c_ext), _fptr(nl_g_ext), _fptr(eta_ext), _fptr(alpha_ext))
+    handle = GC.@preserve dflat vflat sflat nprof nl_c_ext nl_g_ext eta_ext alpha_ext ggp_plan_create(desc)
     ggp_set_state(handle, host_u0)                                                    # u = copy.(prob.u0), :48
 
     # page-lock `result` so that the streaming saves of solve! are asynchronous DMA transfers

@@ -41,12 +41,13 @@
 extern "C" {
 #endif
 
-#define GGP_ABI_VERSION 4u
+#define GGP_ABI_VERSION 5u
+#define GGP_MAX_COMPONENTS 4 /* ncomp <= 2: fused kernels; 3..4: generic plan (ABI 5) */
 
 typedef enum ggp_status {
   GGP_OK = 0,
   GGP_ERR_INVALID = -1,     /* bad descriptor / argument */
-  GGP_ERR_UNSUPPORTED = -2, /* legal in the reference, not covered by this backend (e.g. non power-of-two n) */
+  GGP_ERR_UNSUPPORTED = -2, /* legal in the reference, not covered by this backend (e.g. an axis longer than 8192) */
   GGP_ERR_CUDA = -3,        /* CUDA runtime failure (message in ggp_last_error) */
   GGP_ERR_NCCL = -4,
   GGP_ERR_ALLOC = -5
@@ -66,7 +67,9 @@ typedef enum ggp_table_kind {
 
 typedef enum ggp_nl_kind {
   GGP_NL_NONE = 0,
-  GGP_NL_DIAG = 1 /* G_i(u) = c_i + sum_j g_ij |u_j|^2   (every nonlinearity in test/, examples/, docs/) */
+  GGP_NL_DIAG = 1, /* G_i(u) = c_i + sum_j g_ij |u_j|^2   (every nonlinearity in test/, examples/, docs/) */
+  GGP_NL_MATRIX = 2 /* ABI 5: the closure returned an SMatrix, G_ij(u) = C_ij + sum_k g_ijk |u_k|^2; the half-step applies
+                       the matrix exponential cis(-dt/2 G) (src/kernels.jl:22-25,44).  Coefficients in nl_c_ext / nl_g_ext. */
 } ggp_nl_kind;
 
 typedef enum ggp_pump_kind {
@@ -100,8 +103,9 @@ typedef struct ggp_desc {
   uint32_t struct_size; /* sizeof(ggp_desc) as seen by the caller */
 
   int32_t ndim;         /* number of FFT'd dims, 1..3 (length(lengths)) */
-  int32_t ncomp;        /* M = length(u0), 1 or 2 */
-  int64_t n[3];         /* spatial sizes, n[0] fastest; powers of two */
+  int32_t ncomp;        /* M = length(u0), 1..GGP_MAX_COMPONENTS */
+  int64_t n[3];         /* spatial sizes, n[0] fastest.  Powers of two 2..8192 run on the fused kernels; any other
+                           length up to 4096 runs on the generic plan (Bluestein, ABI 5) */
   int64_t nbatch;       /* trajectories held by THIS plan (product of trailing dims / shards) */
   int64_t batch_offset; /* global index of this plan's first trajectory (Philox counters are global,
                            so results do not depend on the sharding) */
@@ -179,6 +183,19 @@ typedef struct ggp_desc {
      nonlinear phase stay in the plan's precision (documented deviation).  0 = tables in plan precision. */
   int32_t mixed_precision_tables;
   int32_t reserved1;
+
+  /* ABI 5: coefficient arrays for more than two components and for matrix-valued nonlinearities (both run on the
+     generic plan: one kernel per stage of the reference's sequence instead of the fused kernels).  REQUIRED when
+     ncomp > 2 or nl_kind == GGP_NL_MATRIX (the fixed-size arrays above are then ignored), optional otherwise (NULL).
+       nl_c_ext         GGP_NL_DIAG: ncomp x (re,im) c_i (nl_scalar: 1 entry)      GGP_NL_MATRIX: ncomp^2 x (re,im) C_ij, [i][j]
+       nl_g_ext         GGP_NL_DIAG: ncomp^2 x (re,im) g_ij, [i][j] (nl_scalar: ncomp entries g_j)
+                                                                                   GGP_NL_MATRIX: ncomp^3 x (re,im) g_ijk, [i][j][k]
+       noise_eta_ext    ncomp x (re,im)
+       noise_alpha_ext  ncomp^2 x (re,im), [i][j]   (GGP_NOISE_FIELD) */
+  const double *nl_c_ext;
+  const double *nl_g_ext;
+  const double *noise_eta_ext;
+  const double *noise_alpha_ext;
 } ggp_desc;
 
 typedef struct ggp_plan ggp_plan;

@@ -253,7 +253,17 @@ def _cis(x):
         if x.n == 2:
             m11, m21, m12, m22 = exp2x2(1j * x[0, 0], 1j * x[1, 0], 1j * x[0, 1], 1j * x[1, 1])
             return SMatrix([[m11, m12], [m21, m22]])
-        raise NotImplementedError("matrix exponential only restated for 1x1 and 2x2")
+        # M > 2: StaticArrays falls through to the generic scaling-and-squaring Pade algorithm (its `_exp` for
+        # sizes beyond 2x2); scipy.linalg.expm is the same published algorithm (Higham 2005 / Al-Mohy & Higham 2009)
+        import scipy.linalg
+        n = x.n
+        ent = [[np.asarray(x[i, j], dtype=complex) for j in range(n)] for i in range(n)]
+        shape = np.broadcast_shapes(*(e.shape for r in ent for e in r))
+        A = np.stack([np.stack([np.broadcast_to(1j * ent[i][j], shape) for j in range(n)], axis=-1)
+                      for i in range(n)], axis=-2)
+        flat = A.reshape((-1, n, n))
+        E = np.stack([scipy.linalg.expm(m) for m in flat]).reshape(A.shape)
+        return SMatrix([[E[..., i, j] for j in range(n)] for i in range(n)])
     return _cis_scalar(x)
 
 

@@ -316,3 +316,90 @@ def noise_forms(ns, form="field", ndim=1, M=1, N=32, ntraj=3, dtype=np.complex12
                 kwargs=dict(dispersion=dispersion, nonlinearity=nonlinearity, param=param,
                             noise_prototype=proto, position_noise_func=eta),
                 tspan=(0, 0.5), dt=0.05, nsaves=2, save_start=True)
+
+
+def generic(ns, case="np2_1d", dtype=np.complex128, nsteps=6):
+    """Problems that run on the generic plan (generic_plan.cuh): FFT axes of any length (the reference plans FFTW
+    transforms of whatever size u0 has, src/misc.jl:53-58), more than two components (NTuple{M}, src/kernels.jl:31-35)
+    and SMatrix-valued nonlinearities (src/kernels.jl:22-25,44).  sizes are Julia order (n1 fastest); NumPy arrays are
+    (batch, ..., n2, n1)."""
+    real = np.float32 if dtype == np.complex64 else np.float64
+    rng = np.random.default_rng(7)
+    cases = {
+        # case: (sizes, M, batch)
+        "np2_1d": ((100,), 1, ()), "prime_1d": ((127,), 1, (3,)), "np2_2d": ((96, 80), 1, ()),
+        "np2_mixed": ((128, 100), 1, (2,)), "np2_3d": ((24, 20, 18), 1, ()), "np2_long": ((1500,), 1, ()),
+        "m3_vec": ((32, 32), 3, ()), "m3_matdisp": ((64,), 3, (2,)), "m4_mat": ((48,), 4, ()),
+        "rabi": ((32, 32), 2, ()), "rabi_vs": ((32, 32), 2, ()), "rabi_vv": ((32, 32), 2, ()), "rabi_vm": ((32, 32), 2, ()),
+        "m3_np2_noise": ((30, 28), 3, (2,)),
+    }
+    sizes, M, batch = cases[case]
+    nd = len(sizes)
+    L = tuple(real(6.0 + 2 * a) for a in range(nd))
+    shape = batch + tuple(reversed(sizes))
+    axes = [np.arange(n).astype(real) * (L[a] / n) for a, n in enumerate(sizes)]
+    mesh = np.meshgrid(*reversed(axes), indexing="ij")          # slowest axis first
+    r2 = sum((m - L[nd - 1 - i] / 2) ** 2 for i, m in enumerate(mesh))
+    u0 = tuple(((np.exp(-r2 / (2.0 + c)) * (1 + 0.05 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))))
+                * np.exp(0.3j * c)).astype(dtype) for c in range(M))
+    p = SimpleNamespace(g=real(0.8), om=real(0.6), gamma=real(0.05), v=real(0.3))
+    kw = dict(param=p)
+
+    def disp_scalar(ks, p):
+        return _sumsq(ks) / 2 - 1j * p.gamma / 2
+
+    def pot_scalar(rs, p):
+        return p.v * _sumsq(rs) / 10
+
+    def pump_static(rs, p, t):
+        return 0.4 * np.exp(-_sumsq(rs) / 8)
+
+    if case in ("np2_1d", "np2_long"):
+        kw.update(dispersion=disp_scalar, potential=pot_scalar, nonlinearity=lambda u, p: p.g * ns.abs2(u[0]))
+    elif case == "prime_1d":
+        kw.update(dispersion=disp_scalar, nonlinearity=lambda u, p: p.g * ns.abs2(u[0]),
+                  noise_prototype=tuple(np.empty(x.shape, dtype=dtype) for x in u0),
+                  position_noise_func=lambda u, r, p: 0.2 + 0.1 * abs(u[0]))
+    elif case in ("np2_2d", "np2_mixed"):
+        kw.update(dispersion=disp_scalar, nonlinearity=lambda u, p: p.g * (ns.abs2(u[0]) - 0.1j), pump=pump_static)
+    elif case == "np2_3d":
+        kw.update(dispersion=disp_scalar, potential=pot_scalar, nonlinearity=lambda u, p: p.g * ns.abs2(u[0]))
+    elif case == "m3_vec":
+        kw.update(dispersion=lambda ks, p: ns.SVector(_sumsq(ks) / 2, _sumsq(ks) / 3 - 1j * p.gamma, 0.2 + _sumsq(ks) / 4),
+                  potential=lambda rs, p: ns.SVector(p.v * _sumsq(rs) / 10, 0.1, -p.v * rs[0]),
+                  nonlinearity=lambda u, p: ns.SVector(p.g * ns.abs2(u[0]) + 0.5 * ns.abs2(u[2]), 0.3 * ns.abs2(u[1]) - 0.02j,
+                                                       p.g * (ns.abs2(u[0]) + ns.abs2(u[1]) + ns.abs2(u[2]))),
+                  pump=lambda rs, p, t: ns.SVector(0.4 * np.exp(-_sumsq(rs) / 8) * (1 + 0.5 * t), 0 * rs[0], 0.1 + 0 * rs[0]))
+    elif case == "m3_matdisp":
+        kw.update(dispersion=lambda ks, p: ns.SMatrix([[_sumsq(ks) / 2, p.om, 0 * ks[0]],
+                                                       [p.om, _sumsq(ks) / 3 - 1j * p.gamma, 0.5 * p.om],
+                                                       [0 * ks[0], 0.5 * p.om, 0.1 + 0 * ks[0]]]),
+                  nonlinearity=lambda u, p: p.g * (ns.abs2(u[0]) + ns.abs2(u[2])))
+    elif case == "m4_mat":
+        def nl4(u, p):
+            z = 0 * ns.abs2(u[0])
+            return ns.SMatrix([[p.g * ns.abs2(u[0]), p.om + z, z, z],
+                               [p.om + z, p.g * ns.abs2(u[1]) - 0.05j, 0.3 * p.om + z, z],
+                               [z, 0.3 * p.om + z, 0.5 * ns.abs2(u[3]), 0.2j + z],
+                               [z, z, -0.2j + z, p.g * ns.abs2(u[2])]])
+        kw.update(dispersion=disp_scalar, nonlinearity=nl4)
+    elif case.startswith("rabi"):
+        def nl2(u, p):
+            z = 0 * ns.abs2(u[0])
+            return ns.SMatrix([[p.g * ns.abs2(u[0]) + 0.2 * ns.abs2(u[1]), p.om + z],
+                               [p.om + z, p.g * ns.abs2(u[1]) - 0.03j]])
+        kw.update(dispersion=disp_scalar, nonlinearity=nl2, pump=pump_static)
+        if case == "rabi_vs":
+            kw.update(potential=pot_scalar)
+        elif case == "rabi_vv":     # SMatrix nonlinearity x SVector potential: `_mul` gives the mat-vec product (quirk)
+            kw.update(potential=lambda rs, p: ns.SVector(p.v * _sumsq(rs) / 10, 0.2 + 0 * rs[0]))
+        elif case == "rabi_vm":
+            kw.update(potential=lambda rs, p: ns.SMatrix([[p.v * _sumsq(rs) / 10, 0.1 + 0 * rs[0]],
+                                                          [0.1 + 0 * rs[0], 0 * rs[0]]]))
+    elif case == "m3_np2_noise":
+        kw.update(dispersion=disp_scalar,
+                  nonlinearity=lambda u, p: ns.SVector(p.g * ns.abs2(u[0]), p.g * ns.abs2(u[1]), 0.1 * ns.abs2(u[2])),
+                  noise_prototype=tuple(np.empty(x.shape, dtype=dtype) for x in u0),
+                  position_noise_func=lambda u, r, p: ns.SVector(0.2 + 0.1 * abs(u[1]), 0.1, 0.05 * abs(u[0])))
+    dtr = real(0.01)
+    return dict(u0=u0, lengths=L, kwargs=kw, tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=2)

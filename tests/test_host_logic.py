@@ -114,11 +114,22 @@ def test_closure_recognition(G):
     from types import SimpleNamespace
     # every nonlinearity of test/ and examples/ 
     sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * G.abs2(u[0]), SimpleNamespace(g=-6), 1)
-    assert sc and c[0] == 0 and np.isclose(g[0, 0], -6)
+    assert sc == "scalar" and c[0] == 0 and np.isclose(g[0, 0], -6)
     sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * (G.abs2(u[0]) - 1 / p.dx), SimpleNamespace(g=3e-4, dx=2.0), 1)
     assert np.isclose(c[0], -1.5e-4) and np.isclose(g[0, 0], 3e-4)
     sc, c, g = host.recognise_nonlinearity(lambda u, p: G.SVector(0, p.g * G.abs2(u[1])), SimpleNamespace(g=0.015), 2)
-    assert not sc and np.allclose(c, 0) and np.allclose(g, [[0, 0], [0, 0.015]])
+    assert sc == "vector" and np.allclose(c, 0) and np.allclose(g, [[0, 0], [0, 0.015]])
+    # three components (generic plan) and the matrix form: Kerr terms on the diagonal + a constant coupling
+    sc, c, g = host.recognise_nonlinearity(
+        lambda u, p: G.SVector(G.abs2(u[0]) + 2 * G.abs2(u[2]), 0.5 - 0.1j, 3 * G.abs2(u[1])), None, 3)
+    assert sc == "vector" and np.allclose(c, [0, 0.5 - 0.1j, 0]) and np.allclose(g, [[1, 0, 2], [0, 0, 0], [0, 3, 0]])
+    sc, Cm, g3 = host.recognise_nonlinearity(
+        lambda u, p: G.SMatrix([[p.g * G.abs2(u[0]), p.om], [p.om, p.g * G.abs2(u[1]) - 0.3j]]),
+        SimpleNamespace(g=0.7, om=0.25), 2)
+    assert sc == "matrix" and np.allclose(Cm, [[0, 0.25], [0.25, -0.3j]])
+    assert np.allclose(g3[0, 0], [0.7, 0]) and np.allclose(g3[1, 1], [0, 0.7]) and np.allclose(g3[0, 1], 0)
+    with pytest.raises(G.UnsupportedForm):      # spin-exchange terms u_i conj(u_j) are not of the registered form
+        host.recognise_nonlinearity(lambda u, p: G.SMatrix([[0, u[0] * np.conj(u[1])], [np.conj(u[0]) * u[1], 0]]), None, 2)
     sc, c, g = host.recognise_nonlinearity(lambda u, p: p.g * G.abs2(u) / 2, SimpleNamespace(g=0.7), 1)
     assert np.isclose(g[0, 0], 0.35)
     with pytest.raises(G.UnsupportedForm):
