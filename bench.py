@@ -519,7 +519,7 @@ def main():
     lib = G.lib.load()
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("GGP_BENCH_NO_CLOCKS"):      # (A/B switch: does the polling disturb the timing?)
         sampler.start()
 
     # ---- headline workload ---------------------------------------------------------------------

@@ -730,7 +730,8 @@ struct PlanT : PlanBase {
     q6 = d.mixed_precision_tables != 0 && d.table_precision == GGP_C128 && sizeof(T) == 4;
     if (d.slab_nranks > 1) {
       if (ndim != 3 || nbatch != 1) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid without batch dims");
-      if (d.noise_kind != GGP_NOISE_NONE) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition with noise is not supported yet");
+      if (d.noise_kind == GGP_NOISE_FIELD)
+        return fail(GGP_ERR_UNSUPPORTED, "slab decomposition with a field- / position-dependent noise amplitude is not supported");
       P = d.slab_nranks;
       prank = d.slab_rank;
       if (prank < 0 || prank >= P || n[1] % P || n[2] % P) return fail(GGP_ERR_INVALID, "slab: n2 and n3 must be divisible by the number of ranks");
@@ -949,7 +950,9 @@ struct PlanT : PlanBase {
       }
       pw.seed_lo = (uint32_t)d.seed;
       pw.seed_hi = (uint32_t)(d.seed >> 32);
-      pw.elem_offset = batch_offset * nspatial;
+      // global element index of this plan's element 0: trajectory shard, or z-slab (contiguous in the global array),
+      // so the Philox stream does not depend on the decomposition
+      pw.elem_offset = slab ? (long long)prank * nspatial : batch_offset * nspatial;
     }
     has_pointwise = pw.vkind || pw.pump || pw.nl || pw.noise;
     {

@@ -73,6 +73,27 @@ def _worker(rank, world, port, q, mode):
         gathered = [None] * world
         dist.all_gather_object(gathered, sol[0][-1])
         results[name] = np.concatenate(gathered, axis=0)      # z-slabs stack along numpy axis 0
+    # position noise on a slab plan: the Philox counters are global element indices, so the decomposed run must
+    # reproduce the single-GPU run of the same seed (rank 0 runs that one as well)
+    import problems as P
+    pb = P.kerr3d(G, N=32, dtype=np.complex128, nsteps=4)
+    kw = dict(pb["kwargs"], noise_prototype=(np.empty_like(pb["u0"][0]),), position_noise_func=lambda u, r, p: 0.3)
+    prob = G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **kw)
+    it = G.init(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=1, device=rank, slab=(rank, world), rng=77)
+    G.parallel.attach_nccl(G, it, dist)
+    if p2p:
+        G.parallel.attach_p2p(G, it, dist)
+    ts, sol = G.solve_(it)
+    it.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sol[0][-1])
+    if rank == 0:
+        whole = np.concatenate(gathered, axis=0)
+        _, ref = G.solve(prob, G.StrangSplitting(), pb["tspan"], dt=pb["dt"], nsaves=1, device=0, rng=77, show_progress=False)
+        noiseless = G.solve(G.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"]), G.StrangSplitting(),
+                            pb["tspan"], dt=pb["dt"], nsaves=1, device=0, show_progress=False)[1]
+        results["noise_philox_err"] = float(np.linalg.norm((whole - ref[0][-1]).ravel()) / np.linalg.norm(ref[0][-1].ravel()))
+        results["noise_effect"] = float(np.linalg.norm((ref[0][-1] - noiseless[0][-1]).ravel()) / np.linalg.norm(ref[0][-1].ravel()))
     if rank == 0:
         q.put(results)
     dist.barrier()
@@ -106,3 +127,5 @@ def test_slab_decomposition_matches_oracle(mode, world):
         err = np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel())
         tol = 1e-4 if sol[0].dtype == np.complex64 else 1e-10
         assert err <= tol, (name, err)
+    # slab plan with position noise == single-GPU plan with the same seed (and the noise did something)
+    assert results["noise_effect"] > 1e-3 and results["noise_philox_err"] <= 1e-10, (results["noise_philox_err"], results["noise_effect"])
