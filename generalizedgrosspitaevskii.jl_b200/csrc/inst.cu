@@ -104,12 +104,64 @@ static int launch_pdl(void (*k)(const P), unsigned grid, unsigned block, size_t 
   return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
 
+// Wave fit.  A grid of G CTAs at R resident CTAs per SM runs ceil(G / (R * SMs)) waves, the last of them partly empty
+// (C2's contiguous-axis kernel: 2048 CTAs at 8 per SM = 1184 + 864).  If one resident CTA fewer per SM needs no more
+// waves, the waves are fuller and every CTA shares its SM with fewer others: 2048 CTAs at 7 per SM = 1036 + 1012.
+// Occupancy is lowered by asking for more dynamic shared memory than the kernel uses.  MEASURED (r02, profiles/r02_notes.md):
+// it does not pay -- C2's kernel 31.3 us at 8 CTAs per SM, 32.5 at 7, 34.5 at 6, 42.2 at 3: the kernel is bound by
+// latency and wants MORE resident warps, not fuller waves -- so the rule is OFF by default.  GGP_WAVE_FIT=1 switches it
+// on, GGP_ROW_OCC=<n> forces n CTAs per SM for the contiguous-axis kernel.
+template <typename KernelT>
+static size_t wave_fit_smem(KernelT k, unsigned grid, unsigned block, size_t smem) {
+  static const int mode = getenv("GGP_WAVE_FIT") ? atoi(getenv("GGP_WAVE_FIT")) : 0;
+  static const int forced = getenv("GGP_ROW_OCC") ? atoi(getenv("GGP_ROW_OCC")) : 0;
+  if (!mode && !forced) return smem;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  struct Entry { const void* k; unsigned grid, block; size_t smem, out; };
+  thread_local std::vector<Entry> cache;
+  for (const Entry& e : cache)
+    if (e.k == (const void*)k && e.grid == grid && e.block == block && e.smem == smem) return e.out;
+  size_t out = smem;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (int)block, smem) != cudaSuccess) {
+    cudaGetLastError();
+    per_sm = 0;
+  }
+  int want = per_sm;
+  if (forced > 0 && forced < per_sm) {
+    want = forced;
+  } else if (mode && per_sm > 2) {
+    const unsigned long long slots = (unsigned long long)per_sm * sms;
+    const unsigned long long waves = (grid + slots - 1) / slots;
+    // only for grids of a few waves whose last wave is less than 80 % full
+    if (waves >= 2 && waves <= 4 && (unsigned long long)grid * 10 < (waves - 1) * slots * 10 + slots * 8) {
+      int r = per_sm;
+      while (r > 2 && (unsigned long long)(r - 1) * sms * waves >= grid) --r;
+      want = r;
+    }
+  }
+  if (want > 0 && want < per_sm) {
+    // shared memory per SM 228 KB, 1 KB of it reserved per resident CTA: `want` CTAs fit, `want + 1` do not
+    const size_t s = (size_t)233472 / want - 1024;
+    if (s > smem && s <= (size_t)227 * 1024) out = s & ~(size_t)15;
+  }
+  cache.push_back(Entry{(const void*)k, grid, block, smem, out});
+  return out;
+}
+
 template <typename T, int N, int M, int PWV>
 static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   using K = KCfg<T, N, row_E<T>(N, M, PWV)>;
-  const size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
+  size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
   const unsigned grid = (unsigned)((p.nlines + K::LPC - 1) / K::LPC);
   auto k = row_kernel<T, N, M, PWV>;
+  smem = wave_fit_smem(k, grid, K::ROW_THREADS, smem);
   int e = set_smem(k, smem);
   if (e) return e;
   RowParams<T> q = p;

@@ -25,6 +25,9 @@
 #ifndef GGP_STOCH_BUDGET
 #define GGP_STOCH_BUDGET 128
 #endif
+#ifndef GGP_ROW_BUDGET
+#define GGP_ROW_BUDGET 64
+#endif
 #ifndef GGP_DBATCH
 #define GGP_DBATCH 2
 #endif
@@ -230,7 +233,7 @@ struct KCfg {
       return bp < 1 ? 1 : bp;
     }
     const int dr = data_regs(M);
-    const int budget = dr <= 32 ? ((pw_is_stoch(pwv) && EO == 0) ? GGP_STOCH_BUDGET : 64) : ((dr <= 64 && sizeof(T) == 8) ? (pw_is_stoch(pwv) ? 255 : 168) : 255);
+    const int budget = dr <= 32 ? ((pw_is_stoch(pwv) && EO == 0) ? GGP_STOCH_BUDGET : GGP_ROW_BUDGET) : ((dr <= 64 && sizeof(T) == 8) ? (pw_is_stoch(pwv) ? 255 : 168) : 255);
     const int b = 65536 / (ROW_THREADS * budget);
     return b < 1 ? 1 : b;
   }
