@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 #include "kernels.cuh"
+#include "kernels_cp.cuh"
 #include "generic.cuh"
 #ifdef GGP_TMA
 #include "str_tma.cuh"
@@ -158,6 +159,22 @@ static size_t wave_fit_smem(KernelT k, unsigned grid, unsigned block, size_t sme
 template <typename T, int N, int M, int PWV>
 static int launch_row_mp(const RowParams<T>& p, cudaStream_t st) {
   using K = KCfg<T, N, row_E<T>(N, M, PWV)>;
+  if constexpr (M == 2 && !pw_is_stoch(PWV) && CpCfg<T, N>::OK) {
+    // two components: component-parallel kernel (kernels_cp.cuh); GGP_NO_CP=1 keeps the one-thread-both-components kernel
+    static const bool nocp = getenv("GGP_NO_CP") != nullptr;
+    if (!nocp) {
+      using C = CpCfg<T, N>;
+      const size_t smem_cp = (size_t)C::ROW_LPC * 2 * KCfg<T, N>::row_ls() * sizeof(cpx<T>);
+      const unsigned grid_cp = (unsigned)((p.nlines + C::ROW_LPC - 1) / C::ROW_LPC);
+      auto kc = row_cp_kernel<T, N, PWV>;
+      int ec = set_smem(kc, smem_cp);
+      if (ec) return ec;
+      RowParams<T> qc = p;
+      bool usec = false;
+      qc.pdl_pos = pdl_pos_for(pdl_below_one_wave(kc, grid_cp, C::ROW_THREADS, smem_cp), grid_cp, C::ROW_THREADS, &usec);
+      return launch_pdl<RowParams<T>>(kc, grid_cp, C::ROW_THREADS, smem_cp, st, qc, 1, usec);
+    }
+  }
   size_t smem = K::USES_SMEM ? (size_t)K::LPC * M * K::row_ls() * sizeof(cpx<T>) : 0;
   const unsigned grid = (unsigned)((p.nlines + K::LPC - 1) / K::LPC);
   auto k = row_kernel<T, N, M, PWV>;
@@ -259,6 +276,35 @@ int launch_str_tma(int M, StrTmaParams<T> p, long long nfast, long long nother, 
 template <typename T, int N, int M>
 static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaStream_t st) {
   using K = KCfg<T, N>;
+  if constexpr (M == 2 && CpCfg<T, N>::OK && !TwT<T>::split) {
+    // two components: component-parallel kernel (kernels_cp.cuh) for everything but the slab plans' scatter passes
+    static const bool nocp = getenv("GGP_NO_CP") != nullptr;
+    using C = CpCfg<T, N>;
+    if (!nocp && !p.scatter && !p.slab && !p.Dq[0] && nfast % C::STR_W == 0) {
+      p.W = C::STR_W;
+      p.logW = ilog2(C::STR_W);
+      p.LS = K::str_ls(2 * C::STR_W);
+      p.ntx = nfast / C::STR_W;
+      p.tma = 0;
+      p.dl_smem = 0;
+      size_t smem_cp = ((size_t)2 * C::STR_W * p.LS * sizeof(cpx<T>) + 15) & ~(size_t)15;
+      p.tw_smem = 0;
+      if (K::TW_STAGED > 0 && (smem_cp + K::TW_BYTES + 1024) * (size_t)C::STR_MINB <= (size_t)227 * 1024 - 1024 &&
+          !getenv("GGP_NO_TW_SMEM_RT")) {
+        p.tw_smem = 1;
+        smem_cp += K::TW_BYTES;
+      }
+      const long long grid_cp = p.ntx * nother;
+      if (grid_cp > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+      auto kc = str_cp_kernel<T, N>;
+      int ec = set_smem(kc, smem_cp);
+      if (ec) return ec;
+      bool usec = false;
+      p.pdl_pos = pdl_pos_for(pdl_below_one_wave(kc, (unsigned)grid_cp, (unsigned)C::STR_THREADS, smem_cp), (unsigned)grid_cp,
+                              (unsigned)C::STR_THREADS, &usec);
+      return launch_pdl<StrParams<T>>(kc, (unsigned)grid_cp, (unsigned)C::STR_THREADS, smem_cp, st, p, 1, usec);
+    }
+  }
   int W, LS_, threads_, us_;
   str_query<T, N>(M, p.ax, p.slab, nfast, &W, &LS_, &threads_, &us_);
   p.W = W;

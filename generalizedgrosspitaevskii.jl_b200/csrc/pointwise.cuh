@@ -176,7 +176,11 @@ __host__ __device__ constexpr bool pw_has_dense(int pwv) { return pwv == PW_DENS
 // element index (spatial + batch) for noise.
 template <typename T, int M, int PWV>
 __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseParams<T>& p, const HalfStep<T>& h,
-                                                const long long sidx, const long long gidx, const uint4* rnd) {
+                                                const long long sidx, const long long gidx, const uint4* rnd,
+                                                const cpx<T>* spre = nullptr) {
+  // spre: the separable pump profile of this point, already loaded by the caller (one value per component) -- the
+  // component-parallel kernels fetch the profiles of a batch of points together instead of one dependent load per
+  // point and half-step (kernels_cp.cuh)
   if constexpr (PWV == PW_KERR) {
     T n2[M];
 #pragma unroll
@@ -239,6 +243,8 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
       // register-bound two-component row kernels 10 - 22 %, ncu / A-B r02f)
       if (pw_has_dense(PWV) && p.pump_dense) {
         sv[j] = ((const cpx<T>*)h.pd_now[p.pump == 1 ? 0 : j])[sidx];
+      } else if (spre) {
+        sv[j] = spre[j];
       } else {
         sv[j] = p.pump_const ? p.S_const[p.pump == 1 ? 0 : j]
                              : ((p.pump == 2 && p.pump_zero[j]) ? mk<T>((T)0, (T)0) : p.S[p.pump == 1 ? 0 : j][sidx]);

@@ -303,8 +303,9 @@ def test_no_dispersion_and_complex_nonlinearity(G):
 
 
 def test_error_behaviour(G):
-    """Unsupported inputs fail loudly (no CPU fallback): non power-of-two axis, unregistered closure."""
-    u0 = (np.zeros((48, 48), dtype=np.complex128),)
+    """Unsupported inputs fail loudly (no CPU fallback): an axis beyond the built transform sizes (any length up to
+    4096 runs on the generic plan, tests/test_gpu_generic.py), unregistered closure."""
+    u0 = (np.zeros((2, 4100), dtype=np.complex128),)
     disp = lambda ks, p: (ks[0] ** 2 + ks[1] ** 2) / 2
     prob = G.GrossPitaevskiiProblem(u0, (5.0, 5.0), dispersion=disp)
     with pytest.raises(G.GgpError):
