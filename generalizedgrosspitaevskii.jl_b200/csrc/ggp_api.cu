@@ -1662,7 +1662,13 @@ struct PlanT : PlanBase {
 
   // which compile-time variant of the half-step covers this problem (pointwise.cuh)
   int pw_variant() const {
-    if (pw.noise) return (pw.noise_field || pw.pump_dense) ? PW_FIELD : PW_STOCH;
+    if (pw.noise) {
+      if (pw.noise_field || pw.pump_dense) return PW_FIELD;
+      // the Truncated-Wigner shape: everything the general stochastic variant decides per point is fixed (pointwise.cuh)
+      static const bool no_tw = getenv("GGP_NO_TW") != nullptr;
+      if (!no_tw && pw.noise == NOISE_PHILOX && pw.vkind == KIND_NONE && pw.nl != 2 && (!pw.pump || pw.pump_const)) return PW_TW;
+      return PW_STOCH;
+    }
     if (pw.pump_dense) return PW_DENSE;
     if (pw.vkind || pw.pump || pw.nl != 1) return PW_DET;
     return PW_KERR;

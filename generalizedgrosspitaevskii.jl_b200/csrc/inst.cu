@@ -193,6 +193,7 @@ static int launch_row_m(int pwv, const RowParams<T>& p, cudaStream_t st) {
   if (pwv == PW_DET) return launch_row_mp<T, N, M, PW_DET>(p, st);
   if (pwv == PW_STOCH) return launch_row_mp<T, N, M, PW_STOCH>(p, st);
   if (pwv == PW_DENSE) return launch_row_mp<T, N, M, PW_DENSE>(p, st);
+  if (pwv == PW_TW) return launch_row_mp<T, N, M, PW_TW>(p, st);
   return launch_row_mp<T, N, M, PW_FIELD>(p, st);
 }
 
@@ -387,6 +388,7 @@ static int launch_oned_m(int pwv, const OneDParams<T>& p, cudaStream_t st) {
   if (pwv == PW_DET) return launch_oned_mp<T, N, M, PW_DET>(p, st);
   if (pwv == PW_STOCH) return launch_oned_mp<T, N, M, PW_STOCH>(p, st);
   if (pwv == PW_DENSE) return launch_oned_mp<T, N, M, PW_DENSE>(p, st);
+  if (pwv == PW_TW) return launch_oned_mp<T, N, M, PW_STOCH>(p, st);   // (1-D whole-step kernel: the general stochastic variant)
   return launch_oned_mp<T, N, M, PW_FIELD>(p, st);
 }
 

@@ -77,22 +77,29 @@ __device__ __forceinline__ void sincosm1_t(float a, float* s, float* cm1) {
     *cm1 = c - 1.0f;
   }
 }
+// The coefficients live in constant memory: a 64-bit immediate does not fit a DFMA, so as literals every coefficient
+// cost two UMOVs per use -- 24 of the 37 instructions of one evaluation (SASS of the stochastic fp64 row kernel, C4:
+// UMOV was 7.8 % of all executed instructions, ncu r02o); as c[bank][offset] operands they cost none.
+static __constant__ double kSin64[6] = {1.58962301576546568060e-10, -2.50507477628578072866e-8, 2.75573136213857245213e-6,
+                                        -1.98412698295895385996e-4, 8.33333333332211858878e-3, -1.66666666666666307295e-1};
+static __constant__ double kCos64[6] = {-1.13585365213876817300e-11, 2.08757008419747316778e-9, -2.75573141792967388112e-7,
+                                        2.48015872888517045348e-5, -1.38888888888730564116e-3, 4.16666666666665929218e-2};
 __device__ __forceinline__ void sincosm1_t(double a, double* s, double* cm1) {
   if (fabs(a) <= 0.78539816339744830962) {
     const double z = a * a;
-    double ps = 1.58962301576546568060e-10;
-    ps = fma(ps, z, -2.50507477628578072866e-8);
-    ps = fma(ps, z, 2.75573136213857245213e-6);
-    ps = fma(ps, z, -1.98412698295895385996e-4);
-    ps = fma(ps, z, 8.33333333332211858878e-3);
-    ps = fma(ps, z, -1.66666666666666307295e-1);
+    double ps = kSin64[0];
+    ps = fma(ps, z, kSin64[1]);
+    ps = fma(ps, z, kSin64[2]);
+    ps = fma(ps, z, kSin64[3]);
+    ps = fma(ps, z, kSin64[4]);
+    ps = fma(ps, z, kSin64[5]);
     *s = fma(a * z, ps, a);
-    double pc = -1.13585365213876817300e-11;
-    pc = fma(pc, z, 2.08757008419747316778e-9);
-    pc = fma(pc, z, -2.75573141792967388112e-7);
-    pc = fma(pc, z, 2.48015872888517045348e-5);
-    pc = fma(pc, z, -1.38888888888730564116e-3);
-    pc = fma(pc, z, 4.16666666666665929218e-2);
+    double pc = kCos64[0];
+    pc = fma(pc, z, kCos64[1]);
+    pc = fma(pc, z, kCos64[2]);
+    pc = fma(pc, z, kCos64[3]);
+    pc = fma(pc, z, kCos64[4]);
+    pc = fma(pc, z, kCos64[5]);
     *cm1 = fma(z * z, pc, -0.5 * z);
   } else {
     double c;
@@ -168,8 +175,12 @@ __device__ __forceinline__ cpx<T> normal_from(const uint4 r, uint32_t ctr, int r
 //   PW_FIELD  + field- / position-dependent noise amplitude (GGP_NOISE_FIELD); its own variant because the extra
 //             live values cost the constant-amplitude kernel 4 % when they shared one (C4: 8.52 -> 8.88 ms/step)
 //   PW_DENSE  PW_DET + dense time-dependent pump (profiles per half-step, GGP_PUMP_DENSE); with noise: PW_FIELD
-enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2, PW_FIELD = 3, PW_DENSE = 4 };
-__host__ __device__ constexpr bool pw_is_stoch(int pwv) { return pwv == PW_STOCH || pwv == PW_FIELD; }
+//   PW_TW     PW_STOCH for the Truncated-Wigner shape (C4, examples/truncated_wigner.jl): real nonlinearity coefficients
+//             (or none), no potential table, pump none or constant in space, constant noise amplitude, in-kernel Philox.
+//             Everything PW_STOCH decides per point at run time is fixed here: no flag tests, no table pointers, and
+//             the two half-steps of a pair are unrolled (ncu r02o: ISETP + BRA + LDC were 16 % of the executed instructions)
+enum { PW_KERR = 0, PW_DET = 1, PW_STOCH = 2, PW_FIELD = 3, PW_DENSE = 4, PW_TW = 5 };
+__host__ __device__ constexpr bool pw_is_stoch(int pwv) { return pwv == PW_STOCH || pwv == PW_FIELD || pwv == PW_TW; }
 __host__ __device__ constexpr bool pw_has_dense(int pwv) { return pwv == PW_DENSE || pwv == PW_FIELD; }
 
 // One real-space half-step at one grid point.  sidx: index into the spatial tables; gidx: local
@@ -193,6 +204,26 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
       T s, cm1;
       sincosm1_t(-p.dt * gre, &s, &cm1);
       f[i] = rotate_m1(f[i], cm1, s);
+    }
+    return;
+  }
+  if constexpr (PWV == PW_TW) {
+    // u_i <- cis(-dt G_i) (u_i + fnow S) + fnext S - i sqrt(dt) eta_i xi_i  with G real, S constant (zero without a pump)
+    T n2[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) n2[j] = cabs2(f[j]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      T gre = p.nl_c_re[i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) gre = fma_(p.nl_g_re[i][j], n2[j], gre);
+      T s, cm1;
+      sincosm1_t(-p.dt * gre, &s, &cm1);
+      const cpx<T> sv = p.S_const[p.pump == 1 ? 0 : i];
+      const cpx<T> w = f[i] + cmul(h.fnow, sv);
+      cpx<T> r = rotate_m1(w, cm1, s) + cmul(h.fnext, sv);
+      const cpx<T> ex = cmul(p.eta[i], normal_from<T>(rnd[i], h.ctr, p.noise_real));
+      f[i] = r + mk<T>(p.sqrt_dt * ex.y, -p.sqrt_dt * ex.x);
     }
     return;
   }
