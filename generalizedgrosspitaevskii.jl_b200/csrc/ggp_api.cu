@@ -960,6 +960,16 @@ struct PlanT : PlanBase {
       // so the Philox stream does not depend on the decomposition
       pw.elem_offset = slab ? (long long)prank * nspatial : batch_offset * nspatial;
     }
+    // products of plan constants for the Truncated-Wigner variant of the half-step (PW_TW, pointwise.cuh)
+    for (int i = 0; i < M; ++i) {
+      const int src = d.nl_scalar ? 0 : i;
+      const bool has_nl = d.nl_kind == GGP_NL_DIAG;
+      pw.nl_cd[i] = (T)(has_nl ? -(dt / 2) * d.nl_c[src][0] : 0.0);
+      for (int j = 0; j < M; ++j) pw.nl_gd[i][j] = (T)(has_nl ? -(dt / 2) * d.nl_g[src][j][0] : 0.0);
+      const double sq = std::sqrt(dt / 2);
+      pw.eta_s[i] = noise_kind != GGP_NOISE_NONE ? mk<T>((T)(sq * d.noise_eta[i][1]), (T)(-sq * d.noise_eta[i][0]))
+                                                 : mk<T>((T)0, (T)0);
+    }
     has_pointwise = pw.vkind || pw.pump || pw.nl || pw.noise;
     {
       const int eo = size_supported(n[0]) ? row_E_of<T>((int)n[0], M, pw_variant()) : 0;
@@ -1229,6 +1239,15 @@ struct PlanT : PlanBase {
     const double q = dt / 4;  // (dt/2)/2, src/kernels.jl:45-46 with δt = dt/2
     h.fnow = mk<T>((T)(q * a_now.real()), (T)(q * a_now.imag()));
     h.fnext = mk<T>((T)(q * a_next.real()), (T)(q * a_next.imag()));
+    if (pw.pump && pw.pump_const) {   // PW_TW: the pump terms of a spatially constant profile, ready-made
+      for (int i = 0; i < M; ++i) {
+        const cpx<T> sc = pw.S_const[pw.pump == 1 ? 0 : i];
+        const std::complex<double> sv((double)sc.x, (double)sc.y);
+        const std::complex<double> a = q * a_now * sv, b = q * a_next * sv;
+        h.aS[i] = mk<T>((T)a.real(), (T)a.imag());
+        h.bS[i] = mk<T>((T)b.real(), (T)b.imag());
+      }
+    }
     h.ctr = (uint32_t)half_ctr;
     h.ctr_hi = (uint32_t)(half_ctr >> 32);
     h.apply = has_pointwise ? 1 : 0;

@@ -268,13 +268,33 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N, EO>::E],
                                            const long long gidx0, const long long stride) {
   constexpr int E = LineCfg<T, N, EO>::E;
   if constexpr (pw_is_stoch(PWV)) {
+    const HalfStep<T>& href = hs[0].apply ? hs[0] : hs[nh - 1];
+    // pair index = (64-bit half-step counter + 1) >> 1
+    const unsigned long long pair = ((((unsigned long long)href.ctr_hi << 32) | href.ctr) + 1ull) >> 1;
+    if constexpr (PWV == PW_TW && E <= 4) {
+      // both half-steps of the pair in line, element by element; the Philox words of an element are produced right
+      // before they are used and dropped afterwards (held for all elements they were spilled: ncu r02s)
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        uint4 rnd[M];
+        cpx<T> f[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          rnd[c] = philox_for<T>(gidx0 + m * stride + pw.elem_offset, (uint32_t)pair, (uint32_t)(pair >> 32), c, pw.seed_lo,
+                                 pw.seed_hi);
+          f[c] = v[c][m];
+        }
+        if (hs[0].apply) half_step_point<T, M, PWV>(f, pw, hs[0], sidx0 + m * stride, gidx0 + m * stride, rnd);
+        if (nh > 1 && hs[1].apply) half_step_point<T, M, PWV>(f, pw, hs[1], sidx0 + m * stride, gidx0 + m * stride, rnd);
+#pragma unroll
+        for (int c = 0; c < M; ++c) v[c][m] = f[c];
+      }
+      return;
+    }
     // All Philox words of this thread first (E*M independent chains: good ILP), one call per element and
     // component serving both half-steps of the pair; then the half-steps as in the deterministic variant.
     uint4 rnd[E][M];
     if (PWV == PW_TW || pw.noise == NOISE_PHILOX) {
-      const HalfStep<T>& href = hs[0].apply ? hs[0] : hs[nh - 1];
-      // pair index = (64-bit half-step counter + 1) >> 1
-      const unsigned long long pair = ((((unsigned long long)href.ctr_hi << 32) | href.ctr) + 1ull) >> 1;
 #pragma unroll
       for (int m = 0; m < E; ++m)
 #pragma unroll
@@ -282,19 +302,7 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N, EO>::E],
           rnd[m][c] = philox_for<T>(gidx0 + m * stride + pw.elem_offset, (uint32_t)pair, (uint32_t)(pair >> 32), c,
                                     pw.seed_lo, pw.seed_hi);
     }
-    if constexpr (PWV == PW_TW && E <= 4) {
-      // both half-steps of the pair in line, element by element: the Philox words of an element are used and dropped
-#pragma unroll
-      for (int m = 0; m < E; ++m) {
-        cpx<T> f[M];
-#pragma unroll
-        for (int c = 0; c < M; ++c) f[c] = v[c][m];
-        if (hs[0].apply) half_step_point<T, M, PWV>(f, pw, hs[0], sidx0 + m * stride, gidx0 + m * stride, rnd[m]);
-        if (nh > 1 && hs[1].apply) half_step_point<T, M, PWV>(f, pw, hs[1], sidx0 + m * stride, gidx0 + m * stride, rnd[m]);
-#pragma unroll
-        for (int c = 0; c < M; ++c) v[c][m] = f[c];
-      }
-    } else {
+    {
 #pragma unroll 1
       for (int h = 0; h < nh; ++h) {
         if (!hs[h].apply) continue;

@@ -25,6 +25,8 @@ struct HalfStep {
   // (the reference's two pump buffers, src/misc.jl:22-42); fnow = fnext = dt/4
   const void* pd_now[2];
   const void* pd_next[2];
+  // PW_TW: fnow * S and fnext * S for a pump that is constant in space (per component), formed once on the host
+  cpx<T> aS[2], bS[2];
   uint32_t ctr;   // global half-step counter (Philox), low word
   uint32_t ctr_hi;  // bits 32.. of the pair index (folded into the Philox key)
   int apply;      // 0: skip this half-step
@@ -56,6 +58,9 @@ struct PointwiseParams {
   int n1;
   uint32_t seed_lo, seed_hi;
   long long elem_offset;  // global element index of this plan's element 0 (batch_offset * nspatial)
+  // PW_TW: products formed once on the host -- -dt * c_i, -dt * g_ij (real coefficients) and -i sqrt(dt) eta_i
+  T nl_cd[2], nl_gd[2][2];
+  cpx<T> eta_s[2];
 };
 
 // Rotation by the nonlinear phase a = -dt*G, returned as (sin a, cos a - 1).  The phase of one half-step is
@@ -208,22 +213,22 @@ __device__ __forceinline__ void half_step_point(cpx<T> (&f)[M], const PointwiseP
     return;
   }
   if constexpr (PWV == PW_TW) {
-    // u_i <- cis(-dt G_i) (u_i + fnow S) + fnext S - i sqrt(dt) eta_i xi_i  with G real, S constant (zero without a pump)
+    // u_i <- cis(-dt G_i) (u_i + fnow S) + fnext S - i sqrt(dt) eta_i xi_i  with G real, S constant in space (zero
+    // without a pump); every product of plan / half-step constants arrives ready-made (nl_cd, nl_gd, aS, bS, eta_s)
     T n2[M];
 #pragma unroll
     for (int j = 0; j < M; ++j) n2[j] = cabs2(f[j]);
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      T gre = p.nl_c_re[i];
+      T arg = p.nl_cd[i];
 #pragma unroll
-      for (int j = 0; j < M; ++j) gre = fma_(p.nl_g_re[i][j], n2[j], gre);
+      for (int j = 0; j < M; ++j) arg = fma_(p.nl_gd[i][j], n2[j], arg);
       T s, cm1;
-      sincosm1_t(-p.dt * gre, &s, &cm1);
-      const cpx<T> sv = p.S_const[p.pump == 1 ? 0 : i];
-      const cpx<T> w = f[i] + cmul(h.fnow, sv);
-      cpx<T> r = rotate_m1(w, cm1, s) + cmul(h.fnext, sv);
-      const cpx<T> ex = cmul(p.eta[i], normal_from<T>(rnd[i], h.ctr, p.noise_real));
-      f[i] = r + mk<T>(p.sqrt_dt * ex.y, -p.sqrt_dt * ex.x);
+      sincosm1_t(arg, &s, &cm1);
+      const cpx<T> r = rotate_m1(f[i] + h.aS[i], cm1, s) + h.bS[i];
+      const cpx<T> xi = normal_from<T>(rnd[i], h.ctr, p.noise_real);
+      const cpx<T> e = p.eta_s[i];
+      f[i] = mk<T>(fma_(e.x, xi.x, fnma_(e.y, xi.y, r.x)), fma_(e.x, xi.y, fma_(e.y, xi.x, r.y)));
     }
     return;
   }
