@@ -193,7 +193,10 @@ static int launch_row_m(int pwv, const RowParams<T>& p, cudaStream_t st) {
   if (pwv == PW_DET) return launch_row_mp<T, N, M, PW_DET>(p, st);
   if (pwv == PW_STOCH) return launch_row_mp<T, N, M, PW_STOCH>(p, st);
   if (pwv == PW_DENSE) return launch_row_mp<T, N, M, PW_DENSE>(p, st);
-  if (pwv == PW_TW) return launch_row_mp<T, N, M, PW_TW>(p, st);
+  if (pwv == PW_TW) {   // instantiated for one component (the Truncated-Wigner ensembles); two components: general variant
+    if constexpr (M == 1) return launch_row_mp<T, N, M, PW_TW>(p, st);
+    else return launch_row_mp<T, N, M, PW_STOCH>(p, st);
+  }
   return launch_row_mp<T, N, M, PW_FIELD>(p, st);
 }
 

@@ -25,6 +25,9 @@
 #ifndef GGP_STOCH_BUDGET
 #define GGP_STOCH_BUDGET 128
 #endif
+#ifndef GGP_TW_UNROLL_E
+#define GGP_TW_UNROLL_E 4
+#endif
 #ifndef GGP_ROW_BUDGET
 #define GGP_ROW_BUDGET 64
 #endif
@@ -271,7 +274,7 @@ __device__ __forceinline__ void half_steps(cpx<T> (&v)[M][LineCfg<T, N, EO>::E],
     const HalfStep<T>& href = hs[0].apply ? hs[0] : hs[nh - 1];
     // pair index = (64-bit half-step counter + 1) >> 1
     const unsigned long long pair = ((((unsigned long long)href.ctr_hi << 32) | href.ctr) + 1ull) >> 1;
-    if constexpr (PWV == PW_TW && E <= 4) {
+    if constexpr (PWV == PW_TW && E <= GGP_TW_UNROLL_E) {
       // both half-steps of the pair in line, element by element; the Philox words of an element are produced right
       // before they are used and dropped afterwards (held for all elements they were spilled: ncu r02s)
 #pragma unroll
