@@ -3,7 +3,7 @@
 # pipeline at N = 8, and the full default bench line at N = 8.   TAG=r02g bash tools/evidence_8gpu.sh
 TAG=${TAG:-r02g}
 mkdir -p gpurun_out
-(time timeout 900 python -m pytest tests/test_gpu_slab.py -q -x -k "(peer_stores or copy_engines) and (4 or 8)") > gpurun_out/pytest_slab_${TAG}.log 2>&1
+(time timeout 900 python -m pytest tests/test_gpu_slab.py -q -x -k "stores-4 or stores-8 or engines-8") > gpurun_out/pytest_slab_${TAG}.log 2>&1
 tail -4 gpurun_out/pytest_slab_${TAG}.log
 run() {  # name grid env...
   name=$1; grid=$2; shift 2
@@ -12,12 +12,14 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('N=8 grid=$grid %-22s'%'$name', 'chained %.4f ms/step'%d['chained']['ms_per_step'], '%.1f G pt-steps/s'%(d['chained']['value']/1e9))"
 }
+if [ -n "$CHUNK_AB" ]; then
 run chunks1 512 GGP_SLAB_CHUNKS=1
 run chunks4 512 GGP_SLAB_CHUNKS=4
 run chunks4_yocc1 512 GGP_SLAB_CHUNKS=4 GGP_SLAB_YOCC1=1
 run chunks8_yocc1 512 GGP_SLAB_CHUNKS=8 GGP_SLAB_YOCC1=1
 run chunks1 1024 GGP_SLAB_CHUNKS=1
 run chunks4_yocc1 1024 GGP_SLAB_CHUNKS=4 GGP_SLAB_YOCC1=1
+fi
 (time python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 20 --warmup 5) > gpurun_out/bench_${TAG}_n8.json 2> gpurun_out/bench_${TAG}_n8.err
 tail -3 gpurun_out/bench_${TAG}_n8.err
 python - <<PY
