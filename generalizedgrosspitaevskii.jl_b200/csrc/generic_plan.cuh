@@ -972,6 +972,11 @@ static bool gen_wanted(const ggp_desc& d) {
   if (d.ncomp > 2 || d.nl_kind == GGP_NL_MATRIX) return true;
   for (int i = 0; i < d.ndim; ++i)
     if (!size_supported(d.n[i])) return true;   // axes the fused kernels are not instantiated for (any n: Bluestein)
+  // two ComplexF64 components on an 8192-point axis: the fused kernels would need 128 data registers in each of 512
+  // threads per line (more than an SM's register file), the per-component transforms of the generic plan do not
+  if (d.ncomp == 2 && d.precision == GGP_C128)
+    for (int i = 0; i < d.ndim; ++i)
+      if (d.n[i] >= 8192) return true;
   const char* e = getenv("GGP_FORCE_GENERIC");
   return e && atoi(e) != 0;
 }

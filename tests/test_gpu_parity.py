@@ -290,6 +290,32 @@ def test_table_kinds_two_components(G, dkind, vkind):
     assert rel_l2(*outs) <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+@pytest.mark.parametrize("shape,kind", [((8, 16, 64), "full"), ((2, 16, 16, 32), "diag"), ((8, 4096), "full"), ((4096, 8), "full"),
+                                        ((3, 64, 128), "scalar"), ((8192, 4), "diag"), ((4, 8192), "scalar")])
+def test_two_components_geometries(G, shape, kind, dtype):
+    """The component-parallel kernels (csrc/kernels_cp.cuh) over what the C3-shaped tests do not reach: 3-D grids (the
+    forward-only / inverse-only passes of the middle axis), long lines with factorised twiddles on either axis, batch
+    dims, a scalar (separable) dispersion shared by both components, and a Kerr + cross-Kerr nonlinearity with a
+    per-component pump so that the exchange of the half-step matters."""
+    nd = 3 if len(shape) >= 3 and shape[-3] > 3 and kind != "scalar" else 2
+    if shape == (2, 16, 16, 32):
+        nd = 3
+    lengths = (7.0, 11.0, 5.0)[:nd]
+    outs = []
+    for ns in (G, O):
+        pb = _free_problem(ns, shape, lengths, dtype, seed=5, M=2, kind=kind)
+        pb["kwargs"]["nonlinearity"] = lambda u, p, ns=ns: ns.SVector(0.4 * ns.abs2(u[0]) + 0.2 * ns.abs2(u[1]), 0.3 * ns.abs2(u[1]) - 0.01j)
+        # "full": the second component's pump does not follow the first one's envelope -> dense pump route (PW_DENSE);
+        # otherwise S(r) a(t) (PW_DET)
+        sep = 0.0 if kind == "full" else 1.0
+        pb["kwargs"]["pump"] = lambda r, p, t, ns=ns: ns.SVector(0.3 * np.exp(-(r[0] - 3.0) ** 2) * (1 + t),
+                                                                 (0.1 + 0 * r[0]) * (1 + sep * t))
+        prob = ns.GrossPitaevskiiProblem(pb["u0"], pb["lengths"], **pb["kwargs"])
+        outs.append(ns.solve(prob, ns.StrangSplitting(), (0.0, 0.03), dt=0.01, nsaves=1)[1])
+    assert rel_l2(*outs) <= (1e-12 if dtype == np.complex128 else 2e-6)
+
+
 def test_no_dispersion_and_complex_nonlinearity(G):
     """Absent dispersion (AdditiveIdentity -> no FFT at all) and a complex (lossy) nonlinearity."""
     outs = []
