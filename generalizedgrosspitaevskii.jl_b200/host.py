@@ -280,7 +280,9 @@ def exp_table(f, grid, param, dt, M):
             m11, m21, m12, m22 = _expm2(*(1j * (-dt * np.asarray(val[i, j])) for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))))
             cols = [np.broadcast_to(m, shape) for m in (m11, m21, m12, m22)]  # column-major like SMatrix
         else:
-            E = _expm_batched(np.stack([np.stack([np.broadcast_to(1j * (-dt * np.asarray(val[i, j], dtype=complex)), shape)
+            # -dt * D is formed in the closure's own precision first (Float32 dt x Float32 D in a ComplexF32 problem,
+            # as `-δt * f(x, param)` does in src/misc.jl:15); only the exponential runs in double
+            E = _expm_batched(np.stack([np.stack([np.broadcast_to(np.asarray(1j * (-dt * np.asarray(val[i, j])), dtype=complex), shape)
                                                   for j in range(M)], axis=-1) for i in range(M)], axis=-2))
             cols = [E[..., i, j] for j in range(M) for i in range(M)]          # column-major: (1,1) (2,1) ... (M,M)
         kind = L.TABLE_FULL

@@ -403,3 +403,84 @@ def generic(ns, case="np2_1d", dtype=np.complex128, nsteps=6):
                   position_noise_func=lambda u, r, p: ns.SVector(0.2 + 0.1 * abs(u[1]), 0.1, 0.05 * abs(u[0])))
     dtr = real(0.01)
     return dict(u0=u0, lengths=L, kwargs=kw, tspan=(real(0), real(nsteps) * dtr), dt=dtr, nsaves=2)
+
+
+def fuzz(ns, seed=0):
+    """A random legal problem (deterministic in `seed`, identical for every namespace): dimensions, power-of-two and
+    other axis lengths, batch dims, 1-3 components, every table kind, Number / SVector / SMatrix nonlinearities, static /
+    separable / non-separable pumps, constant and field-dependent noise.  Used by tests/test_gpu_fuzz.py to reach
+    combinations nobody wrote a dedicated test for."""
+    rng = np.random.default_rng([20260, seed])
+    pick = lambda xs: xs[int(rng.integers(len(xs)))]
+    nd = pick([1, 1, 2, 2, 3])
+    M = pick([1, 1, 2, 2, 3])
+    dtype = pick([np.complex128, np.complex128, np.complex64])
+    real = np.float32 if dtype == np.complex64 else np.float64
+    pools = {1: [8, 16, 64, 256, 1024, 5, 12, 30, 100, 243], 2: [4, 8, 16, 32, 64, 6, 12, 20, 48], 3: [4, 8, 16, 3, 6, 10]}
+    sizes = tuple(pick(pools[nd]) for _ in range(nd))
+    batch = pick([(), (), (2,), (3,)])
+    L = tuple(real(5.0 + 1.5 * a) for a in range(nd))
+    shape = batch + tuple(reversed(sizes))
+    u0 = tuple(((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * 0.6).astype(dtype) for _ in range(M))
+    c = lambda: real(rng.uniform(0.1, 0.9))
+    kw = {}
+    # dispersion
+    dk = pick(["none", "scalar", "scalar", "diag", "full"]) if M > 1 else pick(["none", "scalar", "scalar", "scalar"])
+    d0, d1, d2, dg = c(), c(), c(), c() * real(0.1)
+    if dk == "scalar":
+        kw["dispersion"] = lambda ks, p: d0 * _sumsq(ks) - 1j * dg
+    elif dk == "diag":
+        kw["dispersion"] = lambda ks, p: ns.SVector(*[(d0 + real(0.2) * i) * _sumsq(ks) - 1j * dg * i for i in range(M)])
+    elif dk == "full":
+        kw["dispersion"] = lambda ks, p: ns.SMatrix([[((d0 + real(0.2) * i) * _sumsq(ks) - 1j * dg) if i == j else d1 * real(0.5) + 0 * ks[0]
+                                                      for j in range(M)] for i in range(M)])
+    # nonlinearity (decides which potential kinds are legal: SVector x SMatrix is a DimensionMismatch, src/kernels.jl:9)
+    nk = pick(["none", "number", "vector", "matrix"]) if M > 1 else pick(["none", "number", "number", "vector"])
+    g0, g1, gl = c(), c(), c() * real(0.05)
+    if nk == "number":
+        kw["nonlinearity"] = lambda u, p: g0 * sum(ns.abs2(u[i]) for i in range(M)) - 1j * gl
+    elif nk == "vector":
+        kw["nonlinearity"] = lambda u, p: ns.SVector(*[g0 * ns.abs2(u[i]) + g1 * ns.abs2(u[(i + 1) % M]) - 1j * gl * i
+                                                       for i in range(M)])
+    elif nk == "matrix":
+        kw["nonlinearity"] = lambda u, p: ns.SMatrix([[(g0 * ns.abs2(u[i]) - 1j * gl) if i == j else g1 + 0 * ns.abs2(u[0])
+                                                       for j in range(M)] for i in range(M)])
+    vk_pool = ["none", "scalar", "diag", "full"] if M > 1 else ["none", "scalar", "scalar"]
+    if nk == "vector" and M > 1:
+        vk_pool = ["none", "scalar", "diag"]
+    vk = pick(vk_pool)
+    v0, v1 = c(), c()
+    if vk == "scalar":
+        kw["potential"] = lambda rs, p: v0 * _sumsq(rs) / 10 - 1j * real(0.01)
+    elif vk == "diag":
+        kw["potential"] = lambda rs, p: ns.SVector(*[(v0 + real(0.1) * i) * rs[0] - 1j * real(0.01) * i for i in range(M)])
+    elif vk == "full":
+        kw["potential"] = lambda rs, p: ns.SMatrix([[(v0 * rs[0] if i == j else v1 * real(0.3) + 0 * rs[0]) for j in range(M)]
+                                                    for i in range(M)])
+    pk = pick(["none", "static", "separable", "dense", "number"])
+    a0 = c()
+    if pk == "static":
+        kw["pump"] = lambda rs, p, t: ns.SVector(*[a0 * np.exp(-_sumsq(rs) / 6) * (i + 1) for i in range(M)]) if M > 1 \
+            else a0 * np.exp(-_sumsq(rs) / 6)
+    elif pk == "separable":
+        kw["pump"] = lambda rs, p, t: ns.SVector(*[a0 * np.exp(-_sumsq(rs) / 6) * (i + 1) * (1 + 3 * t) for i in range(M)]) if M > 1 \
+            else a0 * np.exp(-_sumsq(rs) / 6) * (1 + 3 * t)
+    elif pk == "dense":
+        kw["pump"] = lambda rs, p, t: ns.SVector(*[a0 * np.exp(-(rs[0] - 2 - 10 * t * (i + 1)) ** 2) for i in range(M)]) if M > 1 \
+            else a0 * np.exp(-(rs[0] - 2 - 10 * t) ** 2)
+    elif pk == "number":
+        kw["pump"] = lambda rs, p, t: a0 * (1 + t) + 0 * rs[0]
+    qk = pick(["none", "none", "const", "field"])
+    e0, e1 = c() * real(0.3), c() * real(0.2)
+    noisy = qk != "none"
+    if noisy:
+        real_proto = bool(rng.integers(2))
+        kw["noise_prototype"] = tuple(np.empty(x.shape, dtype=real if real_proto else dtype) for x in u0)
+        if qk == "const":
+            kw["position_noise_func"] = (lambda u, r, p: ns.SVector(*[e0 * (i + 1) for i in range(M)])) if M > 1 else (lambda u, r, p: e0)
+        else:
+            kw["position_noise_func"] = (lambda u, r, p: ns.SVector(*[e0 + e1 * abs(u[(i + 1) % M]) for i in range(M)])) if M > 1 \
+                else (lambda u, r, p: e0 + e1 * abs(u[0]))
+    dtr = real(0.01)
+    desc = f"nd={nd} sizes={sizes} batch={batch} M={M} {np.dtype(dtype).name} D={dk} G={nk} V={vk} F={pk} noise={qk}"
+    return dict(u0=u0, lengths=L, kwargs=kw, tspan=(real(0), real(4) * dtr), dt=dtr, nsaves=2, noisy=noisy, desc=desc)
