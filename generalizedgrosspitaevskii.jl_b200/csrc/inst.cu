@@ -221,6 +221,9 @@ void str_query(int M, int ax, int slab, long long nfast, int* W_, int* LS_, int*
   // gpurun call, both widths with compile-time addresses: cold step 62.45 -> 60.5 us, chained 53.2 -> 52.7.  Not for
   // 1024-point lines (128-thread CTAs: 24.5 -> 25.5 us) and not without TMA (16-byte row pieces with plain loads).
   if (sizeof(T) == 4 && M == 1 && K::TPL == 128 && K::WDEF == 4 && !slab && !getenv("GGP_NO_TMA")) W = 2;
+  // the same for 256-point fp64 lines (32 threads per line; C4): 128-thread CTAs of four columns (64-byte rows), eight
+  // per SM, instead of 256-thread CTAs of eight columns: strided kernel 0.539 -> 0.51 ms per 1024 trajectories (r02z A/B)
+  if (sizeof(T) == 8 && M == 1 && K::TPL == 32 && K::WDEF == 8 && !slab && !getenv("GGP_NO_TMA")) W = 4;
   // z axis of a 3-D grid: consecutive points of a line are a whole xy-plane apart (8 MB at 1024^3), so every row
   // piece of the tile is its own DRAM page and TLB entry; 64-byte pieces instead of 32 halve that cost
   // (1024^3 c64: z pass 17.2 -> 6.7 ms, step 29.4 -> 18.5 ms; 512^3: neutral; 128-byte pieces: slower again)
@@ -364,7 +367,7 @@ static int launch_str_m(StrParams<T> p, long long nfast, long long nother, cudaS
   // the default geometry runs the instantiation with a compile-time tile width (GGP_STR_WRT=1: always the generic one)
   static const bool wrt = getenv("GGP_STR_WRT") != nullptr;
   auto k = (W == K::WDEF && !wrt) ? str_kernel<T, N, M, K::WDEF> : str_kernel<T, N, M, 0>;
-  if constexpr (M == 1 && K::WDEF >= 4 && sizeof(T) == 4) {
+  if constexpr (M == 1 && K::WDEF >= 4) {
     // half the default width, also with compile-time addresses (GGP_STR_W=<WDEF/2>): four smaller CTAs per SM hide the
     // wait for the tile better when the state comes from HBM (2048^2 cold: 40.1 -> 37.1 us per launch, r02y)
     if (W == K::WDEF / 2 && !wrt) k = str_kernel<T, N, M, K::WDEF / 2>;
