@@ -21,6 +21,12 @@
 #ifndef GGP_CP_BUDGET
 #define GGP_CP_BUDGET 64
 #endif
+#ifndef GGP_CP_PREFETCH_D
+#define GGP_CP_PREFETCH_D 0
+#endif
+#ifndef GGP_CP_BP64
+#define GGP_CP_BP64 2
+#endif
 
 namespace ggp {
 
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(CpCfg<T, N>::ROW_THREADS, CpCfg<T, N>::ROW_MIN
 #pragma unroll
     for (int m = 0; m < E; ++m) mine[t + m * TPL] = a[m];
     SYNC::sync();
-    constexpr int BP = sizeof(T) == 8 ? 2 : 4;          // points whose pump profiles are fetched together
+    constexpr int BP = sizeof(T) == 8 ? GGP_CP_BP64 : 4;   // points whose pump profiles are fetched together
     constexpr int HP = E / 2;
     bool pre = false;
     if constexpr (PWV != PW_KERR) pre = p.pw.pump && !p.pw.pump_const && !p.pw.pump_dense;
@@ -218,21 +224,27 @@ __global__ void __launch_bounds__(CpCfg<T, N>::STR_THREADS, CpCfg<T, N>::STR_MIN
       for (int m = 0; m < E; ++m)
         a[m] = cmul(p.Daos ? ldg_nc_ordered(p.Daos + (toff + m * mstride) * p.dcols + c) : ldg_nc_ordered(p.D[c] + toff + m * mstride), a[m]);
     } else if (p.dkind == KIND_FULL) {
-      // u~_c <- D_c0 u~_0 + D_c1 u~_1: this thread needs the other component of its points (planes [col * 2 + row])
-      __syncthreads();  // the last pass may still be reading the lines
-#pragma unroll
-      for (int m = 0; m < E; ++m) mine[t + m * TPL] = a[m];
-      __syncthreads();
+      // u~_c <- D_c0 u~_0 + D_c1 u~_1: this thread needs the other component of its points (planes [col * 2 + row]).
+      // The table entries of the first batch of points are requested BEFORE the exchange, so that their round trip to
+      // L2 / DRAM overlaps the two barriers (the kernel is bound by the latency of these loads: 35 % of its warp samples)
       constexpr int DB = GGP_DBATCH < E ? GGP_DBATCH : E;
-#pragma unroll
-      for (int m0 = 0; m0 < E; m0 += DB) {
-        cpx<T> d[DB][2];
+      auto load_d = [&](cpx<T> (&d)[DB][2], const int m0) {
 #pragma unroll
         for (int b = 0; b < DB; ++b)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             d[b][j] = p.Daos ? ldg_nc_ordered(p.Daos + (toff + (m0 + b) * mstride) * p.dcols + (j * 2 + c))
                              : ldg_nc_ordered(p.D[j * 2 + c] + toff + (m0 + b) * mstride);
+      };
+      cpx<T> d[DB][2];
+      if (GGP_CP_PREFETCH_D) load_d(d, 0);
+      __syncthreads();  // the last pass may still be reading the lines
+#pragma unroll
+      for (int m = 0; m < E; ++m) mine[t + m * TPL] = a[m];
+      __syncthreads();
+#pragma unroll
+      for (int m0 = 0; m0 < E; m0 += DB) {
+        if (!GGP_CP_PREFETCH_D || m0 > 0) load_d(d, m0);
 #pragma unroll
         for (int b = 0; b < DB; ++b) {
           const int m = m0 + b;
