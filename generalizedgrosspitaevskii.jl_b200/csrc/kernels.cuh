@@ -28,6 +28,9 @@
 #ifndef GGP_TW_UNROLL_E
 #define GGP_TW_UNROLL_E 4
 #endif
+#ifndef GGP_ROW_MIN_THREADS
+#define GGP_ROW_MIN_THREADS 128
+#endif
 #ifndef GGP_ROW_BUDGET
 #define GGP_ROW_BUDGET 64
 #endif
@@ -132,7 +135,7 @@ struct KCfg {
   static constexpr int E = L::E;
   static constexpr int TPL = L::TPL;
   static constexpr int G = 128 / (int)sizeof(cpx<T>);  // lanes served by one shared-memory wavefront
-  static constexpr int ROW_THREADS = TPL >= 128 ? TPL : 128;
+  static constexpr int ROW_THREADS = TPL >= GGP_ROW_MIN_THREADS ? TPL : GGP_ROW_MIN_THREADS;
   static constexpr int LPC = ROW_THREADS / TPL;  // lines per CTA (row / 1-D kernels)
   __host__ __device__ static constexpr int row_ls() {
     int ls = L::PADN;
