@@ -734,6 +734,10 @@ struct PlanT : PlanBase {
     dt = d.dt;
     dkind = d.disp_kind;
     q6 = d.mixed_precision_tables != 0 && d.table_precision == GGP_C128 && sizeof(T) == 4;
+    // (more components / matrix-valued nonlinearities run on the generic plan, which has no slab decomposition)
+    if (M > 2) return fail(GGP_ERR_UNSUPPORTED, "more than two components with a slab decomposition are not supported");
+    if (d.nl_kind != GGP_NL_NONE && d.nl_kind != GGP_NL_DIAG)
+      return fail(GGP_ERR_UNSUPPORTED, "matrix-valued nonlinearities with a slab decomposition are not supported");
     if (d.slab_nranks > 1) {
       if (ndim != 3 || nbatch != 1) return fail(GGP_ERR_UNSUPPORTED, "slab decomposition needs a 3-D grid without batch dims");
       if (d.noise_kind == GGP_NOISE_FIELD)
