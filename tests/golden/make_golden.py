@@ -29,6 +29,11 @@ CASES = {
     # field- and position-dependent noise amplitudes (docs/src/stochastic_simulations.md:62-86)
     "noise_field_1d": ("noise_forms", dict(form="field", ndim=1, M=1, N=32, ntraj=3), 7),
     "noise_profile_q2_2d_two_comp": ("noise_forms", dict(form="both", ndim=2, M=2, N=16, ntraj=2), 9),
+    # the generic plan (tests/problems.py: generic): axes of any length, three components with a 3x3 matrix dispersion,
+    # an SMatrix nonlinearity meeting an SVector potential (the matrix-vector product of src/kernels.jl:9,44)
+    "generic_np2_2d": ("generic", dict(case="np2_2d", dtype="complex128"), None),
+    "generic_rabi_vv": ("generic", dict(case="rabi_vv", dtype="complex128"), None),
+    "generic_m3_matdisp": ("generic", dict(case="m3_matdisp", dtype="complex128"), None),
 }
 
 

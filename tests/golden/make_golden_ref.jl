@@ -183,4 +183,26 @@ end
 noise_forms("noise_field_1d", "field", 1, 1)
 noise_forms("noise_profile_q2_2d_two_comp", "both", 2, 2)
 
+function generic_case(case)                                        # problems.generic: the generic plan's shapes
+    p = (; g=0.8, om=0.6, gamma=0.05, v=0.3)
+    disp_scalar(ks, p) = sum(abs2, ks) / 2 - im * p.gamma / 2
+    pump_static(rs, p, t) = 0.4 * exp(-sum(abs2, rs) / 8)
+    dt = 0.01; tspan = (0.0, 6 * dt)
+    prob = if case == "generic_np2_2d"                             # 96 x 80 points: no power of two on either axis
+        nl(u, p) = p.g * (abs2(u[1]) - 0.1im)
+        GrossPitaevskiiProblem(u0_of(case, 1), (6.0, 8.0); dispersion=disp_scalar, nonlinearity=nl, pump=pump_static, param=p)
+    elseif case == "generic_rabi_vv"                               # SMatrix nonlinearity x SVector potential
+        nl2(u, p) = @SMatrix [p.g*abs2(u[1])+0.2*abs2(u[2]) p.om; p.om p.g*abs2(u[2])-0.03im]
+        pot(rs, p) = @SVector [p.v * sum(abs2, rs) / 10, 0.2]
+        GrossPitaevskiiProblem(u0_of(case, 2), (6.0, 8.0); dispersion=disp_scalar, nonlinearity=nl2, potential=pot,
+            pump=pump_static, param=p)
+    else                                                           # three components, 3 x 3 matrix dispersion, 2 trajectories
+        disp3(ks, p) = @SMatrix [sum(abs2, ks)/2 p.om 0; p.om sum(abs2, ks)/3-im*p.gamma 0.5*p.om; 0 0.5*p.om 0.1]
+        nl3(u, p) = p.g * (abs2(u[1]) + abs2(u[3]))
+        GrossPitaevskiiProblem(u0_of(case, 3), (6.0,); dispersion=disp3, nonlinearity=nl3, param=p)
+    end
+    run(case, prob, tspan; dt, nsaves=2)
+end
+foreach(generic_case, ("generic_np2_2d", "generic_rabi_vv", "generic_m3_matdisp"))
+
 println("wrote ", OUT)
