@@ -631,6 +631,18 @@ def main():
                     r3["iter"].close()
                 except Exception as e:
                     extra[key] = dict(error=repr(e))
+            # the generic plan (axes of any length: Bluestein; one kernel per stage): the price of leaving the fused kernels
+            try:
+                rg = measure(G, "c2", 50, 5, local, n=1000, do_e2e=False, do_cold=False)
+                msg = rg["chained_ms"] / 50
+                extra["generic_plan_1000"] = dict(
+                    workload="C2's problem on a 1000^2 grid (not a power of two): generic plan, Bluestein transforms of "
+                             "length 2048, 2d + 2 sweeps per step", value=rg["meta"]["points"] * 50 / (rg["chained_ms"] * 1e-3),
+                    unit=METRIC, ms_per_step=msg, frac_of_hbm_roofline_contract=56 * rg["meta"]["points"] / (msg * 1e-3) / 1e9 / peak)
+                windows += rg["windows"]
+                rg["iter"].close()
+            except Exception as e:
+                extra["generic_plan_1000"] = dict(error=repr(e))
     if extra:
         line["extra"] = extra
 
