@@ -29,6 +29,12 @@ struct GenFftParams {
   int W;                                // lines per CTA
   int LS;                               // shared-memory stride between the lines of a CTA (elements)
   int inverse;
+  // mode 1 (last FFT axis, scalar / SVector exp_D): forward -> x exp_D[k] -> inverse in one launch, the line resident
+  // throughout (the k-space muladd of src/strang_splitting.jl:73-74 fused into the transform; two sweeps fewer per step)
+  int mode;
+  const cpx<T>* D;                      // point-major [k][dcols]
+  int dcols, dcol;
+  long long nspatial;
 };
 
 // thread (xw, t): line blockIdx.x * W + xw, elements t + m * TPL.  Strided axes (sa > 1): xw fastest, so that the
@@ -60,35 +66,57 @@ __global__ void __launch_bounds__(512, 1) gen_fft_kernel(const GenFftParams<T> p
     const int j = t + m * TPL;
     v[m] = (active && j < p.n) ? base[(long long)j * p.sa] : mk<T>((T)0, (T)0);
   }
-  if (p.inverse) {
+  // forward DFT of the n points held in v (zero beyond n), in place
+  auto dft = [&](const bool presync) {
+    if (blu) {
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
-  }
-  if (blu) {
+      for (int m = 0; m < E; ++m) {
+        const int j = t + m * TPL;
+        if (j < p.n) v[m] = cmul(v[m], p.chirp[j]);
+      }
+    }
+    if (presync) fft_line<T, L, -1, SyncBlock, true>(v, t, sl, p.tw);
+    else fft_line<T, L, -1, SyncBlock, false>(v, t, sl, p.tw);
+    if (blu) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        v[m] = cmul(v[m], p.bhat[t + m * TPL]);
+        v[m].y = -v[m].y;
+      }
+      fft_line<T, L, -1, SyncBlock, true>(v, t, sl, p.tw);
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int j = t + m * TPL;
+        v[m].y = -v[m].y;
+        v[m] = j < p.n ? cmul(v[m], p.chirp[j]) : mk<T>((T)0, (T)0);
+      }
+    }
+  };
+  if (p.mode == 1) {
+    dft(false);
+    const long long e0 = inner + outer * p.sa * (long long)p.n;
 #pragma unroll
     for (int m = 0; m < E; ++m) {
       const int j = t + m * TPL;
-      if (j < p.n) v[m] = cmul(v[m], p.chirp[j]);
-    }
-  }
-  fft_line<T, L, -1, SyncBlock, false>(v, t, sl, p.tw);
-  if (blu) {
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-      v[m] = cmul(v[m], p.bhat[t + m * TPL]);
+      if (active && j < p.n) {
+        const long long sidx = (e0 + (long long)j * p.sa) % p.nspatial;
+        v[m] = cmul(p.D[sidx * p.dcols + p.dcol], v[m]);
+      }
       v[m].y = -v[m].y;
     }
-    fft_line<T, L, -1, SyncBlock, true>(v, t, sl, p.tw);
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-      const int j = t + m * TPL;
-      v[m].y = -v[m].y;
-      if (j < p.n) v[m] = cmul(v[m], p.chirp[j]);
-    }
-  }
-  if (p.inverse) {
+    dft(true);
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
+  } else {
+    if (p.inverse) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
+    }
+    dft(false);
+    if (p.inverse) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
+    }
   }
   if (active) {
 #pragma unroll

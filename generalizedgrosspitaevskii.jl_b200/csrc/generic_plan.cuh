@@ -805,11 +805,18 @@ struct GenPlanT : PlanBase {
     ++launches;
     return prof_end();
   }
-  // transform of axis a of one array (nspatial * nbatch elements)
-  int run_fft(cpx<T>* arr, int a, bool inverse) {
-    if (n[a] == 1) return 0;
+  // transform of axis a of one array (nspatial * nbatch elements); dcol >= 0: forward -> x exp_D column dcol -> inverse
+  int run_fft(cpx<T>* arr, int a, bool inverse, int dcol = -1) {
+    if (n[a] == 1 && dcol < 0) return 0;
     GenFftParams<T> q;
     memset(&q, 0, sizeof(q));
+    if (dcol >= 0) {
+      q.mode = 1;
+      q.D = D;
+      q.dcols = ncols_of(dkind, M);
+      q.dcol = dcol;
+      q.nspatial = nspatial;
+    }
     q.u = arr;
     q.tw = tw[a];
     q.chirp = chirp[a];
@@ -902,9 +909,22 @@ struct GenPlanT : PlanBase {
         if ((rc = run_pw(h))) return rc;
         if (half == 0 && dkind != GGP_TABLE_NONE) {
           // diffusion_step! (src/strang_splitting.jl:69-76)
-          if ((rc = run_ft_all(false))) return rc;
-          if ((rc = run_disp())) return rc;
-          if ((rc = run_ft_all(true))) return rc;
+          static const bool nofuse = getenv("GGP_GEN_NOFUSE") != nullptr;
+          const int last = ndim - 1;
+          if (dkind != GGP_TABLE_FULL && n[last] > 1 && !nofuse) {
+            // Number / SVector exp_D: the multiply rides in the transform of the last axis, component by component
+            for (int c = 0; c < M; ++c) {
+              for (int a = 0; a < last; ++a)
+                if ((rc = run_fft(u[c], a, false))) return rc;
+              if ((rc = run_fft(u[c], last, false, dkind == GGP_TABLE_DIAG ? c : 0))) return rc;
+              for (int a = last - 1; a >= 0; --a)
+                if ((rc = run_fft(u[c], a, true))) return rc;
+            }
+          } else {
+            if ((rc = run_ft_all(false))) return rc;
+            if ((rc = run_disp())) return rc;
+            if ((rc = run_ft_all(true))) return rc;
+          }
         }
       }
       if ((rc = window_end())) return rc;
